@@ -1,0 +1,85 @@
+"""oracle/stft_np.py vs CPU torch.stft/istft fixtures (tests/golden/stft_*.npz) and its own
+round-trip properties."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import stft_np
+
+CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "stft_*.npz")))
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(b)
+
+
+def _geom(path):
+    parts = os.path.basename(path)[:-4].split("_")
+    return int(parts[1][1:]), int(parts[2][1:])
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p) for p in CASES])
+def test_stft_matches_torch(path):
+    z = np.load(path); n_fft, hop = _geom(path)
+    S = stft_np.stft(z["y"], n_fft, hop)
+    assert S.shape == z["S"].shape
+    assert rel_l2(S, z["S"]) < 1e-12
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p) for p in CASES])
+def test_istft_matches_torch(path):
+    z = np.load(path); n_fft, hop = _geom(path)
+    w = stft_np.istft(z["z"], hop)
+    assert w.shape == z["w"].shape
+    assert rel_l2(w, z["w"]) < 1e-12
+
+
+@pytest.mark.parametrize("n_fft", [512, 1024, 2048])
+def test_round_trip(n_fft):
+    hop = n_fft // 4
+    rng = np.random.default_rng(n_fft)
+    y = rng.standard_normal(hop * 31)
+    back = stft_np.istft(stft_np.stft(y, n_fft, hop), hop)
+    assert back.shape == y.shape
+    assert rel_l2(back, y) < 1e-12
+
+
+def test_generate_audio_semantics():
+    rng = np.random.default_rng(0)
+    C, T, hop = 256, 24, 128
+    z = rng.standard_normal((C, T)) + 1j * rng.standard_normal((C, T))
+    a = stft_np.generate_audio(z, 16000, hop, is_stft=True)
+    b = stft_np.generate_audio(np.stack([z.real, z.imag]), 16000, hop, is_stft=False)
+    assert a.dtype == np.float32 and a.shape == ((T - 1) * hop,)
+    assert np.array_equal(a, b)
+    assert abs(np.max(np.abs(a)) - 1.0) < 1e-6
+    zero = stft_np.generate_audio(np.zeros((C, T), complex), 16000, hop, is_stft=True)
+    assert not zero.any()
+    bad = z.copy(); bad[3, 3] = np.nan
+    with pytest.raises(ValueError):
+        stft_np.generate_audio(bad, 16000, hop, is_stft=True)
+
+
+def test_spec_and_angle_and_polar_inverse():
+    rng = np.random.default_rng(1)
+    reim = rng.standard_normal((2, 16, 8)).astype(np.float32)
+    sa = stft_np.spec_and_angle(reim)
+    z = stft_np.polar_to_complex(sa[0], sa[1])
+    assert rel_l2(z, reim[0] + 1j * reim[1]) < 1e-12
+
+
+def test_griffin_lim_keeps_reference_quirk():
+    """utils.py:114,127 hand the DC-less magnitude to istft, which then infers
+    n_fft' = 2*(C-1); the loop therefore does not converge -- only shapes, peak
+    normalisation and finiteness are contractual."""
+    rng = np.random.default_rng(2)
+    n_fft, hop = 512, 128
+    y = rng.standard_normal(hop * 23)
+    mag = np.abs(stft_np.stft(y, n_fft, hop))[1:]
+    a1, _, l1 = stft_np.griffin_lim(mag, n_fft, hop, 1, np.random.default_rng(3))
+    a8, s8, l8 = stft_np.griffin_lim(mag, n_fft, hop, 8, np.random.default_rng(3))
+    assert a8.shape == a1.shape and s8.shape == mag.shape
+    assert np.isfinite(a8).all() and np.isfinite(l8) and np.isfinite(l1)
+    assert abs(np.max(np.abs(a8)) - 1.0) < 1e-6
