@@ -55,7 +55,7 @@ def test_loss_matches_reference(path):
 
 def test_state_dict_keys_match_reference():
     z, sd = _load(CASES[0])
-    mine = unet_torch.random_state_dict(8)
+    mine = unet_torch.random_state_dict(sd["model.0.weight"].shape[1])
     assert set(mine) == set(sd)
     for k in sd:
         assert tuple(mine[k].shape) == tuple(sd[k].shape), k
