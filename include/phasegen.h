@@ -1,0 +1,121 @@
+/* phasegen -- C ABI of the B200-native magnitude -> phase -> waveform path.
+ *
+ * The reference (LemonATsu/UNet-PhaseGen) is pure Python and has no FFI of its own; its
+ * "interface" for this path is the Python call surface.  Each entry
+ * point below names the reference call it stands behind.  The Python shims in
+ * unet-phasegen_b200/{model,utils}.py bind these with ctypes.
+ *
+ * Conventions: every function returns 0 (PG_OK) or a negative error code and records a
+ * message retrievable with pg_last_error() (thread-local); no C++ exception crosses the
+ * boundary.  All data pointers are caller-owned DEVICE memory; the library allocates
+ * nothing.  Calls are asynchronous on the given stream (a cudaStream_t passed as void*).
+ * Activations are "channels-last": [clip][row][channel], row = STFT frame / conv position.
+ */
+#ifndef PHASEGEN_H_
+#define PHASEGEN_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_OK 0
+#define PG_ERR_INVALID (-1)
+#define PG_ERR_CUDA (-2)
+#define PG_ERR_UNSUPPORTED (-3)
+
+typedef void* pg_stream;
+
+const char* pg_last_error(void);
+int pg_abi_version(void);
+/* Fails (PG_ERR_UNSUPPORTED) unless the current device is compute capability 10.x. */
+int pg_check_device(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------- STFT front end
+ * Replaces librosa.stft(c, n_fft, hop) + np.delete(.., 0, axis=0) at preproc_mdb.py:93 and
+ * utils.py:120-121, the re/im split of preproc_mdb.py:94-95 (PG_STFT_REIM) and the
+ * abs/log1p/angle of data.py:39-47 (PG_STFT_LOGMAG).  center=True, reflect padding, periodic
+ * Hann of length n_fft.  wave [B][N] fp32 -> out_a/out_b fp32 [B][T][n_fft/2] (frame-major,
+ * DC bin dropped), T = 1 + N/hop.  out_b may be NULL.  op_hi/op_lo (may be NULL): out_a as
+ * bf16 hi/lo planes [B][..][n_fft/2] with op_batch_stride elements between clips -- the
+ * operand of the first convolution.  twiddle: float2[n_fft] = exp(-2*pi*i*m/n_fft).
+ * n_fft in {256,512,1024,2048}, hop = n_fft/4. */
+enum { PG_STFT_LOGMAG = 0, PG_STFT_REIM = 1 };
+int pg_stft_num_frames(int n_samples, int hop);
+int pg_stft(const float* wave, int B, int N, int n_fft, int hop, const float* twiddle, int mode,
+            float* out_a, float* out_b, uint16_t* op_hi, uint16_t* op_lo, int64_t op_batch_stride,
+            pg_stream stream);
+
+/* ---------------------------------------------------------------- ISTFT back end
+ * Replaces utils.generate_audio (utils.py:11-44): zero DC row (:38-39), librosa.istft (:40:
+ * inverse real FFT, periodic Hann, overlap-add, / window sum-of-squares, trim n_fft/2),
+ * finiteness check (:41 -> nonfinite[b] != 0), peak normalisation (:42 -> pg_peak_normalize),
+ * with the polar->complex step of demo.py:39 / train.py:83 fused in (PG_SPEC_POLAR_LOG:
+ * a = log1p-magnitude, b = phase; PG_SPEC_CARTESIAN: a = re, b = im; PG_SPEC_POLAR_MAG:
+ * a = magnitude, b = phase or NULL for zero phase).  Inputs frame-major [B][T][n_fft/2]
+ * (bins 1..n_fft/2); wave [B][(T-1)*hop].  peak [B] (max |wave|) and nonfinite [B] may be NULL. */
+enum { PG_SPEC_POLAR_LOG = 0, PG_SPEC_CARTESIAN = 1, PG_SPEC_POLAR_MAG = 2 };
+int pg_istft(const float* in_a, const float* in_b, int mode, int B, int T, int n_fft, int hop,
+             const float* twiddle, float* wave, float* peak, int* nonfinite, pg_stream stream);
+int pg_peak_normalize(float* wave, const float* peak, int B, int N, pg_stream stream);
+
+/* ---------------------------------------------------------------- U-Net layers
+ * Replace the nn.Conv1d / nn.ConvTranspose1d / norm / activation / torch.cat calls of
+ * model.py:77-113.  A layer is: convolution -> per-channel statistics records -> finalize
+ * (scale, shift) -> apply + activation written as the operand(s) of the consumer(s). */
+enum { PG_CONV = 0, PG_CONV_TRANSPOSE = 1 };
+enum { PG_PREC_FP32_SIMT = 0, PG_PREC_BF16X3 = 1, PG_PREC_BF16 = 2 };
+enum { PG_DT_NONE = 0, PG_DT_F32 = 1, PG_DT_BF16_SPLIT = 2, PG_DT_BF16 = 3 };
+
+typedef struct pg_conv_desc {
+    int kind;                 /* PG_CONV (model.py:77) or PG_CONV_TRANSPOSE (model.py:88,94,101) */
+    int B, C_in, C_out, L_in, L_out, k, stride, pad;
+    int in_rows, in_ld;       /* input buffer: allocated rows per clip (zero beyond L_in), row pitch */
+    int out_rows, out_ld;     /* fp32 output buffer geometry */
+    int precision;            /* PG_PREC_* */
+    int taps_per_group;       /* tensor-core path: taps sharing one activation strip (0 = default 16, 1 = off) */
+    int tc_base_offset_mode;  /* tensor-core path: descriptor base-offset handling of shifted strips */
+    int tc_max_ctas;          /* tensor-core path: cap on the persistent grid (0 = one per SM) */
+} pg_conv_desc;
+
+/* weights: torch layout (Conv1d [C_out][C_in][k], ConvTranspose1d [C_in][C_out][k])
+ * -> bf16 hi/lo planes [k][C_out][C_in] (tensor-core path) and/or fp32 [k][C_in][C_out] (SIMT). */
+int pg_pack_weight(const float* w, int kind, int C_in, int C_out, int k, uint16_t* w_hi,
+                   uint16_t* w_lo, float* w_simt, pg_stream stream);
+
+/* tcgen05 implicit GEMM.  x: bf16 planes [B][in_rows][in_ld]; y fp32 [B][out_rows][out_ld];
+ * stats (may be NULL): float4 {n, mean, M2, 0} [B][P][C_out], P = pg_conv_stat_parts(). */
+int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo,
+               const uint16_t* w_hi, const uint16_t* w_lo, float* y, float* stats, pg_stream stream);
+int pg_conv_stat_parts(const pg_conv_desc* d);
+/* exact fp32 on CUDA cores; x fp32 [B][in_rows][in_ld], w_simt from pg_pack_weight. */
+int pg_conv_simt(const pg_conv_desc* d, const float* x, const float* w_simt, float* y, pg_stream stream);
+int pg_channel_stats(const float* y, int B, int L, int C, int rows, int ld, float* stats, pg_stream stream);
+
+/* train-mode batch norm (model.py:81,83; the reference never calls .eval()): combine the
+ * partial records over (B, L) (per_clip = 0, train.py:42) or over L of each clip
+ * (per_clip = 1, the demo.py:33-42 batch-1 loop).  scale_shift: float2 [G][C], G = per_clip ?
+ * B : 1; mean_var (may be NULL): float2 [G][C] (mean, biased variance). */
+int pg_bn_finalize(const float* stats, int B, int P, int C, int per_clip, const float* gamma,
+                   const float* beta, float eps, float* scale_shift, float* mean_var, pg_stream stream);
+
+typedef struct pg_act_dst {
+    void* hi; void* lo;       /* PG_DT_F32: hi = float*; PG_DT_BF16_SPLIT: two bf16 planes; PG_DT_BF16: hi only */
+    int64_t batch_stride;     /* elements between clips */
+    int ld, ch_off;           /* row pitch and first channel written (skip-concat offset, model.py:113) */
+    int dtype;                /* PG_DT_* */
+    float slope;              /* 0 = ReLU (model.py:82), 0.2 = LeakyReLU (model.py:80), 1 = identity */
+} pg_act_dst;
+/* v = y*scale+shift (scale_shift NULL = identity), then per destination act(v).  C = number
+ * of leading channels of y processed. */
+int pg_bn_act(const float* y, int B, int L, int C, int rows, int ld, const float* scale_shift,
+              int per_clip, const pg_act_dst* dst0, const pg_act_dst* dst1, pg_stream stream);
+
+/* [B][R][S] fp32 -> [B][S][R] fp32 and/or bf16 hi/lo planes (reference [B,C,T] <-> channels-last). */
+int pg_transpose(const float* src, int B, int R, int S, int64_t src_batch_stride, float* dst,
+                 uint16_t* dst_hi, uint16_t* dst_lo, int64_t dst_batch_stride, int dst_ld, pg_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHASEGEN_H_ */

@@ -1,0 +1,46 @@
+"""End-to-end magnitude -> phase -> waveform on the GPU vs the oracle's chain (preproc_mdb.py:93 ->
+data.py:39-47 -> model.py -> demo.py:38-40), including the waveform-SNR criterion of BASELINE.json
+(SNR against the clean input within 0.1 dB of the oracle's)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import stft_np, unet_torch  # noqa: E402
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def snr_db(ref, est):
+    ref = np.asarray(ref, np.float64); est = np.asarray(est, np.float64)
+    g = np.dot(ref, est) / max(np.dot(est, est), 1e-300)        # peak normalisation changes the gain
+    return 10 * np.log10(np.sum(ref ** 2) / np.sum((ref - g * est) ** 2))
+
+
+@pytest.mark.parametrize("n_fft,T,prec", [(256, 40, "bf16x3"), (256, 40, "fp32_simt"), (512, 24, "bf16x3")])
+def test_pipeline_matches_oracle_chain(n_fft, T, prec):
+    import model
+    from phasegen import synth
+    from phasegen.pipeline import PhaseGenPipeline
+    hop, C, B = n_fft // 4, n_fft // 2, 2
+    torch.manual_seed(1)
+    net = model.UNetModel(C, 2 * C).cuda()
+    synth.randomize_norm_affine(net, seed=2)
+    sd = {k: v.detach().cpu() for k, v in net.model.state_dict().items()}
+    wave = synth.synthetic_waves(B, (T - 1) * hop, sr=16000, seed=3, device="cuda")
+    pipe = PhaseGenPipeline(net, n_fft, hop, precision=prec, per_clip=True, phase_only=True)
+    audio, logmag, phase = pipe(wave, check_finite=True, return_intermediates=True)
+    for b in range(B):
+        w = wave[b].cpu().numpy().astype(np.float64)
+        lm = np.log1p(np.abs(stft_np.stft(w, n_fft, hop)[1:]))
+        out = unet_torch.unet_forward(sd, torch.from_numpy(lm)[None], torch.float64, per_clip_bn=True)[0].numpy()
+        ref = stft_np.generate_audio(stft_np.polar_to_complex(lm, out[:C]), 16000, hop, is_stft=True)
+        assert rel_l2(logmag[b].cpu().numpy().T, lm) < 1e-4
+        assert rel_l2(phase[b].cpu().numpy().T, out[:C]) < 1e-3
+        got = audio[b].cpu().numpy()
+        assert rel_l2(got, ref) < 5e-3
+        assert abs(snr_db(w, got) - snr_db(w, ref)) < 0.1

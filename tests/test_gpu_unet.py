@@ -1,0 +1,102 @@
+"""GPU parity of the U-Net forward (model.UNetModel through the C ABI) against the reference-
+generated golden vectors and the oracle.  Bounds (BASELINE.json): fp32-class path relative L2
+<= 1e-3 on the predicted phase; the plain-bf16 path is stated separately at <= 5e-2."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import unet_torch  # noqa: E402
+
+CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "unet_*.npz")))
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def _model_from_sd(sd, C):
+    import model
+    net = model.UNetModel(C, 2 * C).cuda()
+    net.model.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in sd.items()})
+    return net
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p) for p in CASES])
+def test_golden_reference_outputs(path):
+    """Reference model.py outputs (float64) vs the exact-fp32 CUDA path (small channel counts)."""
+    z = np.load(path)
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")}
+    C = z["x"].shape[1]
+    net = _model_from_sd(sd, C)
+    x = torch.from_numpy(z["x"]).float().cuda()
+    out = net.forward(x)                                        # batch statistics (train.py:42)
+    assert out.shape == z["out_batch"].shape
+    assert rel_l2(out.detach().cpu().numpy(), z["out_batch"]) < 1e-4
+    outc = net.forward(x, per_clip=True)                        # demo.py:33-42 semantics
+    assert rel_l2(outc.detach().cpu().numpy(), z["out_clip"]) < 1e-4
+    one = net.forward(x[:1])                                    # literally batch 1
+    assert rel_l2(one.detach().cpu().numpy(), z["out_clip"][:1]) < 1e-4
+
+
+@pytest.mark.parametrize("T", [24, 32, 136])
+@pytest.mark.parametrize("prec,tol_phase", [("bf16x3", 1e-3), ("fp32_simt", 1e-3), ("bf16", 5e-2)])
+def test_tensor_core_unet_vs_oracle(T, prec, tol_phase):
+    import model
+    from phasegen import synth
+    C, B = 64, 3
+    torch.manual_seed(T)
+    net = model.UNetModel(C, 2 * C).cuda()
+    synth.randomize_norm_affine(net, seed=T)
+    net.precision = prec
+    sd = {k: v.detach().cpu() for k, v in net.model.state_dict().items()}
+    x = torch.log1p(torch.randn(B, C, T).abs() * 2.0)
+    for per_clip in (False, True):
+        ref = unet_torch.unet_forward(sd, x, torch.float64, per_clip_bn=per_clip).numpy()
+        out = net.forward(x.cuda(), per_clip=per_clip).detach().cpu().numpy()
+        e_phase, e_all = rel_l2(out[:, :C], ref[:, :C]), rel_l2(out, ref)
+        print(f"T={T} {prec} per_clip={per_clip}: phase rel-L2 {e_phase:.2e}, all {e_all:.2e}")
+        assert e_phase < tol_phase and e_all < tol_phase
+
+
+def test_phase_only_equals_full_forward():
+    import model
+    C, B, T = 128, 2, 40
+    torch.manual_seed(0)
+    net = model.UNetModel(C, 2 * C).cuda()
+    x = torch.log1p(torch.randn(B, T, C).abs()).cuda()           # channels-last entry
+    full = net.forward_channels_last(x, per_clip=True, phase_only=False).clone()
+    ph = net.forward_channels_last(x, per_clip=True, phase_only=True)
+    assert ph.shape == (B, T, C) and full.shape == (B, T, 2 * C)
+    assert torch.equal(ph, full[:, :, :C])
+
+
+def test_time_axis_rule_and_errors():
+    import model
+    net = model.UNetModel(8, 16).cuda()
+    for T in (26, 28, 130):                                     # model.py:113 torch.cat failure in the reference
+        with pytest.raises(RuntimeError, match="Sizes of tensors must match"):
+            net.forward(torch.zeros(1, 8, T, device="cuda"))
+    with pytest.raises(RuntimeError):
+        net.forward(torch.zeros(1, 9, 24, device="cuda"))
+    out = net.forward(torch.randn(2, 8, 24, device="cuda"))
+    assert out.shape == (2, 16, 24) and bool(torch.isfinite(out).all())
+
+
+def test_weights_are_repacked_after_an_update_and_running_stats_move():
+    import model
+    net = model.UNetModel(8, 16).cuda()
+    x = torch.randn(2, 8, 32, device="cuda")
+    a = net.forward(x).clone()
+    rm = net.model.model[4].running_mean.clone()                 # the outermost up-norm (model.4.*)
+    with torch.no_grad():
+        net.model.model[0].weight.mul_(1.5)
+    b = net.forward(x)
+    assert not torch.allclose(a, b)
+    assert int(net.model.model[4].num_batches_tracked) == 2
+    assert not torch.equal(rm, net.model.model[4].running_mean)

@@ -1,0 +1,97 @@
+// Tap tables that turn a Conv1d / ConvTranspose1d into "output position m of phase phi reads
+// input row (m + d) of parity q with weight slab w" -- shared by the tensor-core kernel
+// (conv_tc.cu) and the fp32 SIMT kernel (conv_simt.cu).
+//
+//   Conv1d(k, s, p)            (model.py:77):  y[l]      = sum_k W[k] x[l*s + k - p]
+//       one output phase; input viewed as rows of parity q = (k-p) mod s, row m + (k-p-q)/s.
+//   ConvTranspose1d(k, s, p)   (model.py:88,94,101):  y[l_in*s - p + k] += W[k] x[l_in]
+//       s output phases; phase phi = l mod s uses the taps with (phi + p - k) mod s == 0 and
+//       reads row m + (phi + p - k)/s of the (stride-1) input, l = m*s + phi.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/phasegen.h"
+
+namespace pg {
+
+constexpr int kMaxTaps = 32;
+
+struct ConvTap { int8_t w_idx; int8_t shift; int8_t parity; int8_t pad_; int32_t d; };
+struct ConvGroup { int32_t row0; int8_t parity; int8_t n_taps; int8_t first_tap; int8_t pad_; };
+
+struct ConvPlan {
+    int B, C_in, C_out, L_in, L_out, k;
+    int IS, OS;                 // input row-parity count (conv stride), output phases (convT stride)
+    int n_tile, n_ntiles;       // positions per tile (multiple of 16, <= 256), tiles per phase
+    int n_chunks, n_cotiles;    // C_in / 64, C_out / 128
+    int strip_rows;             // rows of one activation strip (n_tile + largest shift, rounded to 8)
+    int out_rows, out_ld;
+    int n_groups[2], n_taps[2];
+    ConvGroup groups[2][kMaxTaps];
+    ConvTap taps[2][kMaxTaps];
+};
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// Returns PG_OK or PG_ERR_INVALID (message via set_error by the caller's PG_REQUIRE wrappers).
+static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
+    const int s = d->stride, k = d->k, pad = d->pad;
+    if (s < 1 || s > 2 || k < 1 || k > kMaxTaps) { set_error("conv plan: stride must be 1 or 2 and k <= %d (got s=%d k=%d)", kMaxTaps, s, k); return PG_ERR_UNSUPPORTED; }
+    const bool tr = d->kind == PG_CONV_TRANSPOSE;
+    const int L_expect = tr ? (d->L_in - 1) * s - 2 * pad + k : (d->L_in + 2 * pad - k) / s + 1;
+    if (d->L_out != L_expect || d->L_out < 1) { set_error("conv plan: L_out %d does not match geometry (expected %d)", d->L_out, L_expect); return PG_ERR_INVALID; }
+    p->B = d->B; p->C_in = d->C_in; p->C_out = d->C_out; p->L_in = d->L_in; p->L_out = d->L_out; p->k = k;
+    p->IS = tr ? 1 : s;
+    p->OS = tr ? s : 1;
+    p->out_rows = d->out_rows; p->out_ld = d->out_ld;
+    p->n_chunks = d->C_in / 64; p->n_cotiles = d->C_out / 128;
+    const int l_max = (d->L_out + p->OS - 1) / p->OS;
+    p->n_ntiles = (l_max + 255) / 256;
+    p->n_tile = (((l_max + p->n_ntiles - 1) / p->n_ntiles) + 15) / 16 * 16;
+    int tpg = d->taps_per_group <= 0 ? 16 : d->taps_per_group;
+    int max_shift = 0;
+    for (int phi = 0; phi < 2; ++phi) { p->n_groups[phi] = 0; p->n_taps[phi] = 0; }
+    for (int phi = 0; phi < p->OS; ++phi) {
+        // collect (parity, d, w) and sort by (parity, d)
+        ConvTap t[kMaxTaps]; int n = 0;
+        for (int kk = 0; kk < k; ++kk) {
+            ConvTap e; e.w_idx = (int8_t)kk; e.shift = 0; e.pad_ = 0;
+            if (tr) {
+                int num = phi + pad - kk;
+                if (((num % s) + s) % s != 0) continue;
+                e.parity = 0; e.d = floordiv(num, s);
+            } else {
+                int off = kk - pad;
+                int q = ((off % s) + s) % s;
+                e.parity = (int8_t)q; e.d = (off - q) / s;
+            }
+            t[n++] = e;
+        }
+        for (int i = 1; i < n; ++i) {           // insertion sort
+            ConvTap e = t[i]; int j = i - 1;
+            while (j >= 0 && (t[j].parity > e.parity || (t[j].parity == e.parity && t[j].d > e.d))) { t[j + 1] = t[j]; --j; }
+            t[j + 1] = e;
+        }
+        int ng = 0, i = 0;
+        while (i < n) {
+            ConvGroup g; g.parity = t[i].parity; g.row0 = t[i].d; g.first_tap = (int8_t)i; g.pad_ = 0;
+            int j = i;
+            while (j < n && t[j].parity == g.parity && (j - i) < tpg && (t[j].d - g.row0) < tpg &&
+                   (p->n_tile + (t[j].d - g.row0) <= 256)) {
+                t[j].shift = (int8_t)(t[j].d - g.row0);
+                if (t[j].shift > max_shift) max_shift = t[j].shift;
+                ++j;
+            }
+            g.n_taps = (int8_t)(j - i);
+            p->groups[phi][ng++] = g;
+            i = j;
+        }
+        for (int q = 0; q < n; ++q) p->taps[phi][q] = t[q];
+        p->n_groups[phi] = ng; p->n_taps[phi] = n;
+    }
+    p->strip_rows = (p->n_tile + max_shift + 7) / 8 * 8;
+    if (p->strip_rows > 256) p->strip_rows = 256;
+    return PG_OK;
+}
+
+}  // namespace pg

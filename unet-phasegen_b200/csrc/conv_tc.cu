@@ -1,0 +1,440 @@
+// Implicit-GEMM Conv1d / ConvTranspose1d on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+// Reference path replaced: the eight nn.Conv1d / nn.ConvTranspose1d calls of
+// /root/reference/model.py:77-78,88-89,94-95,101-102 (library cuDNN/oneDNN kernels there).
+//
+// Formulation.  Activations are channels-last bf16 [B][rows][C] stored as two planes
+// (hi, lo; x = hi + lo to 2^-16), weights are packed [tap][C_out][C_in] as two planes too.
+// One CTA tile is  D[128 output channels][N output positions of one clip and one output
+// phase], accumulated in TMEM (fp32) over K = (tap, 64-channel chunk):
+//     D += Whi*Xhi + Whi*Xlo + Wlo*Xhi          (n_terms = 3, "fp32-class": rel. error ~2^-16)
+//     D += Whi*Xhi                              (n_terms = 1, plain bf16)
+// Operands reach shared memory by TMA with 128-byte swizzle, K-major:
+//   A (weights)    : box {64 ci, 128 co, 1 tap}
+//   B (activations): box {64 ci, 1 parity, R rows, 1 clip}.  The zero padding of the
+//     convolution is TMA's out-of-bounds zero fill (row coordinate < 0 or >= extent), the
+//     stride-2 convolutions read the even/odd row view of the same buffer (parity dim), and a
+//     stride-2 transposed convolution is two interleaved output phases, each a stride-1
+//     correlation over the taps of matching parity.
+//   "Strip" reuse: consecutive taps read the same rows shifted by one, so one activation strip
+//   of N + shift rows is loaded per (chunk, tap group) and every tap of the group issues its
+//   MMAs from a descriptor whose start address is advanced by shift*128 B inside the swizzle
+//   pattern.  taps_per_group = 1 disables the trick (one strip per tap).
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5
+// epilogue: TMEM -> registers -> per-channel partial batch-norm statistics (count, mean, M2;
+// two passes over TMEM so the variance is centred) and the raw fp32 output, channels-last.
+// Persistent: grid = min(#tiles, #SMs); the tile order keeps co-resident CTAs on the same
+// weight slab (L2 reuse).  Two TMEM accumulators (2 x 256 columns) overlap epilogue and MMA.
+#include <cuda.h>
+
+#include <cstdio>
+
+#include "common.cuh"
+#include "conv_plan.h"
+
+namespace pg {
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trapped launch (reported error) rather than a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins) {
+        if ((spins & 1023u) == 0 && clock64() - t0 > 4000000000ll) {   // ~2 s at 1.9 GHz
+            printf("phasegen conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n",
+                   (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread for the CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives once every MMA issued so far by this thread has completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, K-major, 128-byte swizzle (8-row x 128 B atoms, 1024 B apart).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, int base_offset_mode) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                // [0,14)  start address >> 4
+    d |= (uint64_t)0 << 16;                                 // [16,30) leading byte offset (unused: one atom along K)
+    d |= (uint64_t)(1024 >> 4) << 32;                       // [32,46) stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                                 // [46,48) descriptor version (sm_100)
+    if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;   // [49,52) base offset
+    d |= (uint64_t)2 << 61;                                 // [61,64) SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, M = 128.
+__device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------ kernel
+struct ConvTcParams {
+    ConvPlan plan;                  // tap tables, tile geometry (conv_plan.h)
+    float* y;                       // [B][out_rows][out_ld] raw conv output (fp32)
+    float4* stats;                  // [B][P][C_out] {n, mean, M2, 0}, P = OS * n_ntiles; may be null
+    int n_a_slots;                  // A ring depth
+    int b_slot_bytes;               // bytes of one plane of a B strip (R * 128)
+    int n_terms;                    // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi
+    int base_offset_mode;           // descriptor base-offset handling for shifted strips
+};
+
+constexpr int kThreads = 192;
+constexpr int kATileBytes = 128 * 128;        // one plane: 128 co x 64 ci bf16
+constexpr int kMaxASlots = 6;
+
+struct TileCoord { int co_tile, phase, b, nt; };
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvPlan& p, int tile) {
+    TileCoord c;
+    int per_slab = p.B * p.n_ntiles;
+    int slab = tile / per_slab, r = tile % per_slab;
+    c.co_tile = slab / p.OS; c.phase = slab % p.OS;
+    c.b = r / p.n_ntiles; c.nt = r % p.n_ntiles;
+    return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+               const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+               const __grid_constant__ ConvTcParams prm) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const ConvPlan& pl = prm.plan;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int nA = prm.n_a_slots;
+    const int bPlane = prm.b_slot_bytes;
+    uint8_t* a_base = smem;                                   // nA x {hi 16 KB, lo 16 KB}
+    uint8_t* b_base = a_base + (size_t)nA * 2 * kATileBytes;  // 2 x {hi bPlane, lo bPlane}
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + 4 * (size_t)bPlane);
+    uint64_t* fullA = bars;                   // [kMaxASlots]
+    uint64_t* emptyA = bars + kMaxASlots;     // [kMaxASlots]
+    uint64_t* fullB = bars + 2 * kMaxASlots;  // [2]
+    uint64_t* emptyB = fullB + 2;             // [2]
+    uint64_t* accFull = emptyB + 2;           // [2]
+    uint64_t* accEmpty = accFull + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accEmpty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = pl.n_cotiles * pl.OS * pl.B * pl.n_ntiles;
+    const bool three = prm.n_terms == 3;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_x_hi);
+        if (three) { tma_prefetch_desc(&map_w_lo); tma_prefetch_desc(&map_x_lo); }
+        for (int i = 0; i < nA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(fullB + i, 1); mbar_init(emptyB + i, 1);
+            mbar_init(accFull + i, 1); mbar_init(accEmpty + i, 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            uint32_t a_it = 0, b_it = 0;
+            const uint32_t a_bytes = (three ? 2 : 1) * kATileBytes;
+            const uint32_t b_bytes = (three ? 2 : 1) * (uint32_t)bPlane;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                TileCoord tc = decode_tile(pl, tile);
+                const int m0 = tc.nt * pl.n_tile;
+                const int ng = pl.n_groups[tc.phase];
+                for (int ch = 0; ch < pl.n_chunks; ++ch) {
+                    for (int g = 0; g < ng; ++g) {
+                        const ConvGroup grp = pl.groups[tc.phase][g];
+                        {
+                            const int s = b_it & 1; const uint32_t ph = (b_it >> 1) & 1;
+                            mbar_wait(emptyB + s, ph ^ 1);
+                            mbar_expect_tx(fullB + s, b_bytes);
+                            uint8_t* dst = b_base + (size_t)s * 2 * bPlane;
+                            tma_load_4d(dst, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b);
+                            if (three) tma_load_4d(dst + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b);
+                            ++b_it;
+                        }
+                        for (int j = 0; j < grp.n_taps; ++j) {
+                            const ConvTap tp = pl.taps[tc.phase][grp.first_tap + j];
+                            const int s = a_it % nA; const uint32_t ph = (a_it / nA) & 1;
+                            mbar_wait(emptyA + s, ph ^ 1);
+                            mbar_expect_tx(fullA + s, a_bytes);
+                            uint8_t* dst = a_base + (size_t)s * 2 * kATileBytes;
+                            tma_load_3d(dst, &map_w_hi, fullA + s, ch * 64, tc.co_tile * 128, tp.w_idx);
+                            if (three) tma_load_3d(dst + kATileBytes, &map_w_lo, fullA + s, ch * 64, tc.co_tile * 128, tp.w_idx);
+                            ++a_it;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================================================================= MMA issuer
+        if (lane == 0) {
+            uint32_t a_it = 0, b_it = 0, t_it = 0;
+            const uint32_t idesc = make_idesc_bf16(pl.n_tile);
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_it) {
+                TileCoord tc = decode_tile(pl, tile);
+                const int acc = t_it & 1; const uint32_t acc_ph = (t_it >> 1) & 1;
+                mbar_wait(accEmpty + acc, acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                const int ng = pl.n_groups[tc.phase];
+                uint32_t accumulate = 0;
+                for (int ch = 0; ch < pl.n_chunks; ++ch) {
+                    for (int g = 0; g < ng; ++g) {
+                        const ConvGroup grp = pl.groups[tc.phase][g];
+                        const int bs = b_it & 1; const uint32_t bph = (b_it >> 1) & 1;
+                        mbar_wait(fullB + bs, bph);
+                        tc_fence_after();
+                        const uint32_t b_hi = smem_u32(b_base + (size_t)bs * 2 * bPlane);
+                        const uint32_t b_lo = b_hi + bPlane;
+                        for (int j = 0; j < grp.n_taps; ++j) {
+                            const ConvTap tp = pl.taps[tc.phase][grp.first_tap + j];
+                            const int as = a_it % nA; const uint32_t aph = (a_it / nA) & 1;
+                            mbar_wait(fullA + as, aph);
+                            tc_fence_after();
+                            const uint32_t a_hi = smem_u32(a_base + (size_t)as * 2 * kATileBytes);
+                            const uint32_t a_lo = a_hi + kATileBytes;
+                            const uint32_t sh = (uint32_t)tp.shift * 128u;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {       // 4 x (K = 16) per 64-channel chunk
+                                const uint64_t da_hi = make_desc_sw128(a_hi + kk * 32, 0);
+                                const uint64_t db_hi = make_desc_sw128(b_hi + sh + kk * 32, prm.base_offset_mode);
+                                if (three) {
+                                    const uint64_t da_lo = make_desc_sw128(a_lo + kk * 32, 0);
+                                    const uint64_t db_lo = make_desc_sw128(b_lo + sh + kk * 32, prm.base_offset_mode);
+                                    umma_bf16(d_tmem, da_lo, db_hi, idesc, accumulate);
+                                    umma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
+                                    umma_bf16(d_tmem, da_hi, db_hi, idesc, 1);
+                                } else {
+                                    umma_bf16(d_tmem, da_hi, db_hi, idesc, accumulate);
+                                }
+                                accumulate = 1;
+                            }
+                            umma_commit(emptyA + as);
+                            ++a_it;
+                        }
+                        umma_commit(emptyB + bs);
+                        ++b_it;
+                    }
+                }
+                umma_commit(accFull + acc);
+            }
+        }
+    } else {
+        // ========================================================================= epilogue
+        const int q = warp & 3;                               // TMEM lane quarter this warp may read
+        uint32_t t_it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_it) {
+            TileCoord tc = decode_tile(pl, tile);
+            const int acc = t_it & 1; const uint32_t acc_ph = (t_it >> 1) & 1;
+            const int m0 = tc.nt * pl.n_tile;
+            const int l_phase = (pl.L_out - tc.phase + pl.OS - 1) / pl.OS;   // positions of this phase
+            int n_valid = l_phase - m0; if (n_valid > pl.n_tile) n_valid = pl.n_tile; if (n_valid < 0) n_valid = 0;
+            mbar_wait(accFull + acc, acc_ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+            const int co = tc.co_tile * 128 + q * 32 + lane;
+            // pass 1: mean over the valid columns
+            float sum = 0.f;
+            for (int c0 = 0; c0 < n_valid; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) if (c0 + i < n_valid) sum += v[i];
+            }
+            const float mean = n_valid > 0 ? sum / (float)n_valid : 0.f;
+            // pass 2: centred second moment + store
+            float m2 = 0.f;
+            float* yrow = prm.y + ((size_t)tc.b * pl.out_rows) * pl.out_ld + co;
+            for (int c0 = 0; c0 < n_valid; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (c0 + i < n_valid) {
+                        float d = v[i] - mean;
+                        m2 += d * d;
+                        const int row = (m0 + c0 + i) * pl.OS + tc.phase;
+                        yrow[(size_t)row * pl.out_ld] = v[i];
+                    }
+                }
+            }
+            if (prm.stats) {
+                const int P = pl.OS * pl.n_ntiles;
+                const int p = tc.phase * pl.n_ntiles + tc.nt;
+                prm.stats[((size_t)tc.b * P + p) * pl.C_out + co] = make_float4((float)n_valid, mean, m2, 0.f);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accEmpty + acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static int encode_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, const char* what) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return PG_ERR_CUDA; }
+    cuuint64_t d[5], s[5]; cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), d, s, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r); return PG_ERR_CUDA; }
+    return PG_OK;
+}
+
+static int g_sm_count = 0, g_max_smem = 0;
+
+}  // namespace pg
+
+extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi,
+                          const uint16_t* w_lo, float* y, float* stats, pg_stream stream) {
+    using namespace pg;
+    PG_REQUIRE(d && x_hi && w_hi && y, "pg_conv_tc: null pointer");
+    PG_REQUIRE(d->precision == PG_PREC_BF16X3 || d->precision == PG_PREC_BF16, "pg_conv_tc: precision must be BF16X3 or BF16");
+    const bool three = d->precision == PG_PREC_BF16X3;
+    PG_REQUIRE(!three || (x_lo && w_lo), "pg_conv_tc: lo planes required for BF16X3");
+    PG_REQUIRE(d->C_in % 64 == 0 && d->C_out % 128 == 0, "pg_conv_tc: needs C_in %% 64 == 0 and C_out %% 128 == 0 (got %d, %d)", d->C_in, d->C_out);
+    PG_REQUIRE(d->in_ld % 8 == 0, "pg_conv_tc: input row pitch must be a multiple of 8 elements");
+    ConvTcParams prm;
+    int rc = conv_plan_build(d, &prm.plan);
+    if (rc != PG_OK) return rc;
+    const ConvPlan& pl = prm.plan;
+    if (!g_sm_count) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    prm.y = y; prm.stats = reinterpret_cast<float4*>(stats);
+    prm.n_terms = three ? 3 : 1;
+    prm.base_offset_mode = d->tc_base_offset_mode;
+    prm.b_slot_bytes = pl.strip_rows * 128;
+    const int fixed = 4 * prm.b_slot_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    int nA = (g_max_smem - fixed) / (2 * kATileBytes);
+    if (nA > kMaxASlots) nA = kMaxASlots;
+    PG_REQUIRE(nA >= 2, "pg_conv_tc: strip of %d rows leaves no room for the weight ring", pl.strip_rows);
+    prm.n_a_slots = nA;
+    const size_t smem_bytes = (size_t)fixed + (size_t)nA * 2 * kATileBytes;
+
+    CUtensorMap mw_hi, mw_lo, mx_hi, mx_lo;
+    {
+        // weights [tap][C_out][C_in] bf16
+        uint64_t dims[3] = {(uint64_t)d->C_in, (uint64_t)d->C_out, (uint64_t)d->k};
+        uint64_t str[2] = {(uint64_t)d->C_in * 2, (uint64_t)d->C_in * d->C_out * 2};
+        uint32_t box[3] = {64, 128, 1};
+        if ((rc = encode_bf16(&mw_hi, w_hi, 3, dims, str, box, "w_hi")) != PG_OK) return rc;
+        if ((rc = encode_bf16(&mw_lo, three ? w_lo : w_hi, 3, dims, str, box, "w_lo")) != PG_OK) return rc;
+    }
+    {
+        // activations [B][in_rows][in_ld] viewed as {channel, parity, row / IS, clip}
+        const int IS = pl.IS;
+        uint64_t dims[4] = {(uint64_t)d->C_in, (uint64_t)IS, (uint64_t)((d->L_in + IS - 1) / IS), (uint64_t)d->B};
+        uint64_t str[3] = {(uint64_t)d->in_ld * 2, (uint64_t)d->in_ld * 2 * IS, (uint64_t)d->in_rows * d->in_ld * 2};
+        uint32_t box[4] = {64, 1, (uint32_t)pl.strip_rows, 1};
+        PG_REQUIRE(d->in_rows >= ((d->L_in + IS - 1) / IS) * IS, "pg_conv_tc: in_rows %d too small for L_in %d at stride %d", d->in_rows, d->L_in, IS);
+        if ((rc = encode_bf16(&mx_hi, x_hi, 4, dims, str, box, "x_hi")) != PG_OK) return rc;
+        if ((rc = encode_bf16(&mx_lo, three ? x_lo : x_hi, 4, dims, str, box, "x_lo")) != PG_OK) return rc;
+    }
+    static size_t configured = 0;
+    if (smem_bytes > configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) { set_error("conv_tc: cannot opt in to %zu bytes of shared memory: %s", smem_bytes, cudaGetErrorString(e)); return PG_ERR_CUDA; }
+        configured = smem_bytes;
+    }
+    const int n_tiles = pl.n_cotiles * pl.OS * pl.B * pl.n_ntiles;
+    int grid = n_tiles < g_sm_count ? n_tiles : g_sm_count;
+    if (d->tc_max_ctas > 0 && grid > d->tc_max_ctas) grid = d->tc_max_ctas;
+    conv_tc_kernel<<<grid, kThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(mw_hi, mw_lo, mx_hi, mx_lo, prm);
+    return check_launch("conv_tc_kernel");
+}

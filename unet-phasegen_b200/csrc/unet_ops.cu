@@ -1,0 +1,268 @@
+// U-Net glue kernels around the convolutions (all HBM-bound, channels-last):
+//   * pg_conv_simt      exact-fp32 CUDA-core convolution (small channel counts, GPU-side check)
+//   * pg_channel_stats  per-(clip, channel) {n, mean, M2} of a conv output (SIMT path; the
+//                       tensor-core kernel produces the same records in its epilogue)
+//   * pg_bn_finalize    combine partial records (Chan) -> per-channel scale/shift of the
+//                       train-mode batch norm of model.py:81,83 (batch or per-clip statistics)
+//   * pg_bn_act         y*scale+shift, ReLU / LeakyReLU(0.2) (model.py:80,82), written as the
+//                       next layer's operand(s): fp32 or bf16 hi/lo planes, at a channel offset
+//                       (this is how the skip concat of model.py:113 is materialised)
+//   * pg_pack_weight    torch Conv/ConvT weight layouts -> [tap][C_out][C_in] planes
+//   * pg_transpose      [B][R][S] -> [B][S][R] (reference [B,C,T] layout <-> channels-last)
+#include "common.cuh"
+#include "conv_plan.h"
+
+namespace pg {
+
+// ---------------------------------------------------------------------------- SIMT conv
+constexpr int kSimtPos = 4;
+
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(const __grid_constant__ ConvPlan pl, const float* __restrict__ x, int in_rows, int in_ld,
+                 const float* __restrict__ w, float* __restrict__ y) {
+    const int co = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m0 = (blockIdx.y * blockDim.y + threadIdx.y) * kSimtPos;
+    const int b = blockIdx.z / pl.OS, phase = blockIdx.z % pl.OS;
+    const int l_phase = (pl.L_out - phase + pl.OS - 1) / pl.OS;
+    if (co >= pl.C_out || m0 >= l_phase) return;
+    float acc[kSimtPos];
+#pragma unroll
+    for (int i = 0; i < kSimtPos; ++i) acc[i] = 0.f;
+    const float* xb = x + (size_t)b * in_rows * in_ld;
+    for (int t = 0; t < pl.n_taps[phase]; ++t) {
+        const ConvTap tp = pl.taps[phase][t];
+        const float* wp = w + (size_t)tp.w_idx * pl.C_in * pl.C_out + co;
+        const float* xr[kSimtPos];
+        bool ok[kSimtPos];
+#pragma unroll
+        for (int i = 0; i < kSimtPos; ++i) {
+            int row = (m0 + i + tp.d) * pl.IS + tp.parity;
+            ok[i] = row >= 0 && row < pl.L_in && (m0 + i) < l_phase;
+            xr[i] = xb + (size_t)(ok[i] ? row : 0) * in_ld;
+        }
+        for (int ci = 0; ci < pl.C_in; ++ci) {
+            const float wv = __ldg(wp + (size_t)ci * pl.C_out);
+#pragma unroll
+            for (int i = 0; i < kSimtPos; ++i)
+                if (ok[i]) acc[i] = fmaf(__ldg(xr[i] + ci), wv, acc[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kSimtPos; ++i) {
+        if (m0 + i < l_phase) {
+            int row = (m0 + i) * pl.OS + phase;
+            y[((size_t)b * pl.out_rows + row) * pl.out_ld + co] = acc[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------- channel stats
+__global__ void channel_stats_kernel(const float* __restrict__ y, int L, int C, int rows, int ld, float4* __restrict__ stats) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (c >= C) return;
+    const float* p = y + (size_t)b * rows * ld + c;
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += p[(size_t)l * ld];
+    const float mean = s / (float)L;
+    float m2 = 0.f;
+    for (int l = 0; l < L; ++l) { float d = p[(size_t)l * ld] - mean; m2 += d * d; }
+    stats[(size_t)b * C + c] = make_float4((float)L, mean, m2, 0.f);
+}
+
+// --------------------------------------------------------------------------- BN finalize
+__global__ void bn_finalize_kernel(const float4* __restrict__ stats, int B, int P, int C, int per_clip,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float2* __restrict__ scale_shift, float2* __restrict__ mean_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (c >= C) return;
+    const int b0 = per_clip ? g : 0, b1 = per_clip ? g + 1 : B;
+    double n = 0.0, mean = 0.0, m2 = 0.0;
+    for (int b = b0; b < b1; ++b)
+        for (int p = 0; p < P; ++p) {
+            const float4 r = stats[((size_t)b * P + p) * C + c];
+            if (r.x <= 0.f) continue;
+            const double nb = r.x, d = (double)r.y - mean, nn = n + nb;
+            mean += d * nb / nn;
+            m2 += (double)r.z + d * d * n * nb / nn;
+            n = nn;
+        }
+    const double var = n > 0.0 ? m2 / n : 0.0;
+    const double sc = (gamma ? (double)gamma[c] : 1.0) / sqrt(var + (double)eps);
+    const double sh = (beta ? (double)beta[c] : 0.0) - mean * sc;
+    scale_shift[(size_t)g * C + c] = make_float2((float)sc, (float)sh);
+    if (mean_var) mean_var[(size_t)g * C + c] = make_float2((float)mean, (float)var);
+}
+
+// ------------------------------------------------------------------------------- BN + act
+struct ActDst {
+    void* hi; void* lo; long long batch_stride; int ld; int ch_off; int dtype; float slope;
+};
+
+__device__ __forceinline__ void store_act4(const ActDst& d, int b, int l, int c, float4 v) {
+    v.x = leaky(v.x, d.slope); v.y = leaky(v.y, d.slope); v.z = leaky(v.z, d.slope); v.w = leaky(v.w, d.slope);
+    const size_t o = (size_t)b * d.batch_stride + (size_t)l * d.ld + d.ch_off + c;
+    if (d.dtype == PG_DT_F32) {
+        *reinterpret_cast<float4*>(static_cast<float*>(d.hi) + o) = v;
+    } else {
+        __nv_bfloat16 h[4], lo[4];
+        split_bf16(v.x, h[0], lo[0]); split_bf16(v.y, h[1], lo[1]);
+        split_bf16(v.z, h[2], lo[2]); split_bf16(v.w, h[3], lo[3]);
+        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(d.hi) + o) = *reinterpret_cast<uint2*>(h);
+        if (d.dtype == PG_DT_BF16_SPLIT) *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(d.lo) + o) = *reinterpret_cast<uint2*>(lo);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_kernel(const float* __restrict__ y, int L, int C, int rows, int ld, const float2* __restrict__ scale_shift,
+              int per_clip, ActDst d0, ActDst d1) {
+    const int c4 = C >> 2;
+    const size_t total = (size_t)L * c4;
+    const int b = blockIdx.y;
+    const float2* ss = scale_shift ? scale_shift + (size_t)(per_clip ? b : 0) * C : nullptr;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int l = (int)(i / c4), c = (int)(i % c4) * 4;
+        float4 v = *reinterpret_cast<const float4*>(y + ((size_t)b * rows + l) * ld + c);
+        if (ss) {
+            const float4 s01 = *reinterpret_cast<const float4*>(ss + c);
+            const float4 s23 = *reinterpret_cast<const float4*>(ss + c + 2);
+            v.x = fmaf(v.x, s01.x, s01.y); v.y = fmaf(v.y, s01.z, s01.w);
+            v.z = fmaf(v.z, s23.x, s23.y); v.w = fmaf(v.w, s23.z, s23.w);
+        }
+        if (d0.dtype) store_act4(d0, b, l, c, v);
+        if (d1.dtype) store_act4(d1, b, l, c, v);
+    }
+}
+
+// --------------------------------------------------------------------------- weight pack
+__global__ void pack_weight_kernel(const float* __restrict__ w, int transposed, int C_in, int C_out, int k,
+                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ simt) {
+    const size_t total = (size_t)k * C_out * C_in;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % C_in);
+        const int co = (int)((i / C_in) % C_out);
+        const int t = (int)(i / ((size_t)C_in * C_out));
+        // Conv1d weight [C_out][C_in][k]; ConvTranspose1d weight [C_in][C_out][k]
+        const float v = transposed ? w[((size_t)ci * C_out + co) * k + t] : w[((size_t)co * C_in + ci) * k + t];
+        if (hi) {
+            __nv_bfloat16 h, l;
+            split_bf16(v, h, l);
+            hi[i] = h;
+            if (lo) lo[i] = l;
+        }
+        if (simt) simt[((size_t)t * C_in + ci) * C_out + co] = v;
+    }
+}
+
+// ----------------------------------------------------------------------------- transpose
+__global__ void transpose_kernel(const float* __restrict__ src, int R, int S, long long src_batch_stride,
+                                 float* __restrict__ dst, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                 long long dst_batch_stride, int dst_ld) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const float* sp = src + (size_t)b * src_batch_stride;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int r = r0 + j, s = s0 + threadIdx.x;
+        tile[j][threadIdx.x] = (r < R && s < S) ? sp[(size_t)r * S + s] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int s = s0 + j, r = r0 + threadIdx.x;
+        if (s < S && r < R) {
+            const float v = tile[threadIdx.x][j];
+            const size_t o = (size_t)b * dst_batch_stride + (size_t)s * dst_ld + r;
+            if (dst) dst[o] = v;
+            if (hi) {
+                __nv_bfloat16 h, l;
+                split_bf16(v, h, l);
+                hi[o] = h;
+                if (lo) lo[o] = l;
+            }
+        }
+    }
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" int pg_conv_simt(const pg_conv_desc* d, const float* x, const float* w_simt, float* y, pg_stream stream) {
+    PG_REQUIRE(d && x && w_simt && y, "pg_conv_simt: null pointer");
+    ConvPlan pl;
+    pg_conv_desc dd = *d;
+    dd.taps_per_group = 1;
+    int rc = conv_plan_build(&dd, &pl);
+    if (rc != PG_OK) return rc;
+    const int bx = pl.C_out >= 64 ? 64 : 32;
+    dim3 block(bx, 256 / bx);
+    const int l_max = (pl.L_out + pl.OS - 1) / pl.OS;
+    dim3 grid((pl.C_out + bx - 1) / bx, (l_max + block.y * kSimtPos - 1) / (block.y * kSimtPos), pl.B * pl.OS);
+    PG_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "pg_conv_simt: grid too large");
+    conv_simt_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pl, x, d->in_rows, d->in_ld, w_simt, y);
+    return check_launch("conv_simt_kernel");
+}
+
+extern "C" int pg_channel_stats(const float* y, int B, int L, int C, int rows, int ld, float* stats, pg_stream stream) {
+    PG_REQUIRE(y && stats && B > 0 && L > 0 && C > 0 && B <= 65535, "pg_channel_stats: bad arguments");
+    dim3 grid((C + 127) / 128, B);
+    channel_stats_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, L, C, rows, ld, reinterpret_cast<float4*>(stats));
+    return check_launch("channel_stats_kernel");
+}
+
+extern "C" int pg_bn_finalize(const float* stats, int B, int P, int C, int per_clip, const float* gamma, const float* beta,
+                              float eps, float* scale_shift, float* mean_var, pg_stream stream) {
+    PG_REQUIRE(stats && scale_shift && B > 0 && P > 0 && C > 0 && B <= 65535, "pg_bn_finalize: bad arguments");
+    dim3 grid((C + 127) / 128, per_clip ? B : 1);
+    bn_finalize_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(stats), B, P, C, per_clip, gamma, beta, eps,
+        reinterpret_cast<float2*>(scale_shift), reinterpret_cast<float2*>(mean_var));
+    return check_launch("bn_finalize_kernel");
+}
+
+static int to_dst(const pg_act_dst* s, int C, ActDst* o, const char* which) {
+    o->dtype = 0; o->hi = o->lo = nullptr; o->batch_stride = 0; o->ld = 0; o->ch_off = 0; o->slope = 1.f;
+    if (!s || s->dtype == PG_DT_NONE) return PG_OK;
+    PG_REQUIRE(s->dtype == PG_DT_F32 || s->dtype == PG_DT_BF16_SPLIT || s->dtype == PG_DT_BF16, "pg_bn_act: %s: bad dtype %d", which, s->dtype);
+    PG_REQUIRE(s->hi && (s->dtype != PG_DT_BF16_SPLIT || s->lo), "pg_bn_act: %s: null plane", which);
+    PG_REQUIRE(s->ld % 4 == 0 && s->ch_off % 4 == 0 && s->batch_stride % 4 == 0 && s->ch_off + C <= s->ld, "pg_bn_act: %s: misaligned or too narrow destination", which);
+    o->hi = s->hi; o->lo = s->lo; o->batch_stride = s->batch_stride; o->ld = s->ld; o->ch_off = s->ch_off; o->dtype = s->dtype; o->slope = s->slope;
+    return PG_OK;
+}
+
+extern "C" int pg_bn_act(const float* y, int B, int L, int C, int rows, int ld, const float* scale_shift, int per_clip,
+                         const pg_act_dst* dst0, const pg_act_dst* dst1, pg_stream stream) {
+    PG_REQUIRE(y && B > 0 && L > 0 && C > 0 && B <= 65535, "pg_bn_act: bad arguments");
+    PG_REQUIRE(C % 4 == 0 && ld % 4 == 0, "pg_bn_act: channel count and pitch must be multiples of 4");
+    ActDst d0, d1;
+    int rc;
+    if ((rc = to_dst(dst0, C, &d0, "dst0")) != PG_OK) return rc;
+    if ((rc = to_dst(dst1, C, &d1, "dst1")) != PG_OK) return rc;
+    const size_t total = (size_t)L * (C / 4);
+    int gx = (int)((total + 255) / 256); if (gx > 1024) gx = 1024;
+    bn_act_kernel<<<dim3(gx, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        y, L, C, rows, ld, reinterpret_cast<const float2*>(scale_shift), per_clip, d0, d1);
+    return check_launch("bn_act_kernel");
+}
+
+extern "C" int pg_pack_weight(const float* w, int kind, int C_in, int C_out, int k, uint16_t* w_hi, uint16_t* w_lo,
+                              float* w_simt, pg_stream stream) {
+    PG_REQUIRE(w && (w_hi || w_simt) && C_in > 0 && C_out > 0 && k > 0, "pg_pack_weight: bad arguments");
+    const size_t total = (size_t)k * C_out * C_in;
+    int gx = (int)((total + 255) / 256); if (gx > 148 * 16) gx = 148 * 16;
+    pack_weight_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        w, kind == PG_CONV_TRANSPOSE, C_in, C_out, k, reinterpret_cast<__nv_bfloat16*>(w_hi),
+        reinterpret_cast<__nv_bfloat16*>(w_lo), w_simt);
+    return check_launch("pack_weight_kernel");
+}
+
+extern "C" int pg_transpose(const float* src, int B, int R, int S, int64_t src_batch_stride, float* dst, uint16_t* dst_hi,
+                            uint16_t* dst_lo, int64_t dst_batch_stride, int dst_ld, pg_stream stream) {
+    PG_REQUIRE(src && (dst || dst_hi) && B > 0 && R > 0 && S > 0 && B <= 65535 && dst_ld >= R, "pg_transpose: bad arguments");
+    dim3 grid((S + 31) / 32, (R + 31) / 32, B);
+    transpose_kernel<<<grid, dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        src, R, S, src_batch_stride, dst, reinterpret_cast<__nv_bfloat16*>(dst_hi), reinterpret_cast<__nv_bfloat16*>(dst_lo),
+        dst_batch_stride, dst_ld);
+    return check_launch("transpose_kernel");
+}

@@ -1,0 +1,229 @@
+"""Drop-in for the reference's ``model.py``: same classes, constructor signatures, attributes
+and checkpoint keys (``UNetModel`` model.py:22-54, ``UNetBlock`` model.py:57-113), with the
+forward pass executed by the hand-written sm_100a kernels of libphasegen.so.
+
+What is kept from the reference interface
+  * ``UNetModel(input_nc, output_nc, norm_layer=nn.BatchNorm2d, gpu_ids=[])``, ``.forward(x)``
+    with x float32 ``[B, C, T]`` on the GPU -> ``[B, 2C, T]`` (``out[:, :C]`` raw phase,
+    ``out[:, C:]`` log-magnitude estimate, train.py:45), ``.save(path)``, ``.load(path)``,
+    ``.model`` (the outermost block), ``.gpu_ids``.
+  * ``UNetBlock(outer_nc, inner_nc, k_size, stride, padding, input_nc, cat_nc, submodule, pos,
+    norm_layer, transpose)`` with the same nesting, so ``model.state_dict()`` has exactly the
+    reference's keys and shapes and reference checkpoints load.
+  * train-mode normalisation statistics on every call (the reference never calls ``.eval()``),
+    over (B, L) like train.py:42.  ``forward(x, per_clip=True)`` computes them per clip -- what
+    the demo.py:33-42 batch-1 loop produces -- so a whole batch of clips can be inferred at once.
+  * a time axis that breaks a skip concat raises RuntimeError, as torch.cat does at model.py:113.
+
+What differs: the modules inside a block only *hold parameters*; arithmetic happens in
+``phasegen.unet.UNetExecutor``.  There is no CPU path: a non-CUDA input raises.
+"""
+import functools
+
+import torch
+import torch.nn as nn
+
+from phasegen import unet as _unet
+from phasegen._lib import PG_CONV, PG_CONV_TRANSPOSE
+# model.py:7 of the reference imports these names from utils; keep them importable from here too.
+from utils import Pool, GANLoss, View, EnergyLoss, Transpose, Flatten  # noqa: F401
+
+
+def weights_init(m):
+    """N(0, 0.02) initialiser of model.py:12-20 (defined there, never called)."""
+    name = type(m).__name__
+    if "Conv" in name or "Linear" in name:
+        nn.init.normal_(m.weight.data, 0.0, 0.02)
+    elif "BatchNorm2d" in name:
+        nn.init.normal_(m.weight.data, 1.0, 0.02)
+        nn.init.constant_(m.bias.data, 0.0)
+
+
+def _norm_needs_bias(norm_layer):
+    base = norm_layer.func if isinstance(norm_layer, functools.partial) else norm_layer
+    return base == nn.InstanceNorm2d
+
+
+class UNetBlock(nn.Module):
+    """One U-Net level.  ``self.model`` is an ``nn.Sequential`` whose slot order reproduces the
+    reference's so that parameter names match; it is a parameter container, not a compute graph
+    (calling it directly runs stock PyTorch ops and is not the product path)."""
+
+    def __init__(self, outer_nc, inner_nc, k_size, stride, padding, input_nc=None, cat_nc=None,
+                 submodule=None, pos=None, norm_layer=nn.BatchNorm2d, transpose=None):
+        super().__init__()
+        self.pos = pos
+        self.outermost = pos == "outermost"
+        bias = _norm_needs_bias(norm_layer)
+        input_nc = outer_nc if input_nc is None else input_nc
+        transpose = padding if transpose is None else transpose
+        cat_nc = inner_nc * 2 if cat_nc is None else cat_nc
+        innermost = pos == "innermost"
+
+        down = nn.Conv1d(input_nc, inner_nc, kernel_size=k_size, stride=stride, padding=padding, bias=bias)
+        up = nn.ConvTranspose1d(inner_nc if innermost else cat_nc, outer_nc,
+                                kernel_size=k_size + 1 if innermost else k_size,
+                                stride=stride, padding=transpose, bias=bias)
+        down_norm = None if (self.outermost or innermost) else norm_layer(inner_nc)
+        up_norm = norm_layer(outer_nc)
+
+        slots = []
+        if not self.outermost:
+            slots.append(nn.LeakyReLU(0.2, True))
+        slots.append(down)
+        if down_norm is not None:
+            slots.append(down_norm)
+        if not innermost:
+            slots.append(submodule)
+        slots += [nn.ReLU(True), up, up_norm]
+        self.model = nn.Sequential(*slots)
+        # un-registered handles for the executor (registering them would duplicate state_dict keys)
+        self.__dict__["_parts"] = dict(down=down, down_norm=down_norm, up=up, up_norm=up_norm,
+                                       sub=None if innermost else submodule)
+
+    def forward(self, x):
+        raise RuntimeError("UNetBlock is executed through UNetModel.forward (phasegen kernels); "
+                           "a block on its own has no product path")
+
+
+def _conv_spec(m, kind):
+    if m.bias is not None:
+        raise RuntimeError("phasegen: convolution bias (InstanceNorm configuration) is not supported")
+    return _unet.ConvSpec(kind, m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0], m.padding[0])
+
+
+class _NoBackward(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, out, *params):
+        return out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, grad):
+        raise NotImplementedError("phasegen: the backward pass of UNetModel is not available in this build")
+
+
+class UNetModel(nn.Module):
+    precision = "auto"     # "auto" | "bf16x3" (fp32-class, 3 bf16 tensor-core products) | "bf16" | "fp32_simt"
+    phase_only = False     # compute only out[:, :C] of the last layer (what demo.py:38 / train.py:78 use)
+
+    def __init__(self, input_nc, output_nc, norm_layer=nn.BatchNorm2d, gpu_ids=[]):
+        super().__init__()
+        self.gpu_ids = gpu_ids
+        nc = input_nc
+        blk = UNetBlock(nc * 2, nc * 4, 4, 2, 1, pos="innermost", norm_layer=norm_layer)
+        blk = UNetBlock(nc * 2, nc * 2, 8, 2, 1, cat_nc=nc * 4, submodule=blk, norm_layer=norm_layer)
+        blk = UNetBlock(nc * 2, nc * 2, 8, 1, 2, cat_nc=nc * 4, submodule=blk, norm_layer=norm_layer)
+        blk = UNetBlock(output_nc, nc * 2, 32, 2, 16, input_nc=nc, cat_nc=nc * 4, submodule=blk,
+                        pos="outermost", norm_layer=norm_layer)
+        self.model = blk
+        self.__dict__["_exec"] = {}
+        self.__dict__["_packed"] = {}
+
+    # ------------------------------------------------------------------ structure helpers
+    def _blocks(self):
+        out, b = [], self.model
+        while b is not None:
+            out.append(b)
+            b = b._parts["sub"]
+        return out
+
+    def _levels(self):
+        return [_unet.LevelSpec(_conv_spec(b._parts["down"], PG_CONV), b._parts["down_norm"] is not None,
+                                _conv_spec(b._parts["up"], PG_CONV_TRANSPOSE), True) for b in self._blocks()]
+
+    def _resolve_precision(self, levels):
+        if self.precision != "auto":
+            return self.precision
+        return "bf16x3" if _unet.tc_supported(levels) else "fp32_simt"
+
+    def executor(self, B, T, device, per_clip=False, phase_only=None, **kw):
+        levels = self._levels()
+        prec = kw.pop("precision", None) or self._resolve_precision(levels)
+        phase_only = self.phase_only if phase_only is None else phase_only
+        c_final = levels[0].up.C_out // 2 if phase_only else None
+        if c_final is not None and prec != "fp32_simt" and c_final % 128:
+            c_final = None      # tensor-core tiles are 128 channels wide; fall back to the full layer
+        key = (B, T, str(device), prec, per_clip, c_final, tuple(sorted(kw.items())))
+        ex = self._exec.get(key)
+        if ex is None:
+            ex = _unet.UNetExecutor(levels, B, T, device, prec, per_clip, out_channels=c_final, **kw)
+            self._exec[key] = ex
+            self._packed.pop(id(ex), None)
+        self._ensure_packed(ex)
+        return ex
+
+    def _ensure_packed(self, ex):
+        blocks = self._blocks()
+        ws = [b._parts["down"].weight for b in blocks] + [b._parts["up"].weight for b in blocks]
+        stamp = tuple((w.data_ptr(), w._version) for w in ws)
+        if self._packed.get(id(ex)) != stamp:
+            ex.pack_weights(ws[:len(blocks)], ws[len(blocks):])
+            self._packed[id(ex)] = stamp
+
+    def _norm_params(self, device):
+        dn, up = [], []
+        for b in self._blocks():
+            for lst, m in ((dn, b._parts["down_norm"]), (up, b._parts["up_norm"])):
+                if m is None:
+                    lst.append(None)
+                    continue
+                gamma = m.weight.detach() if getattr(m, "weight", None) is not None else None
+                beta = m.bias.detach() if getattr(m, "bias", None) is not None else None
+                lst.append((gamma, beta, float(getattr(m, "eps", 1e-5))))
+        return dn, up
+
+    def _update_running_stats(self, ex):
+        """Train-mode side effect of nn.BatchNorm (momentum update of the running buffers)."""
+        for i, b in enumerate(self._blocks()):
+            for m, mv, desc in ((b._parts["down_norm"], ex.dn_mv[i], ex.dn_desc[i]), (b._parts["up_norm"], ex.up_mv[i], ex.up_desc[i])):
+                if m is None or mv is None or not getattr(m, "track_running_stats", False) or m.running_mean is None:
+                    continue
+                if mv.shape[1] != m.running_mean.numel():
+                    continue
+                n = desc.B * desc.L_out
+                mom = m.momentum if m.momentum is not None else 0.1
+                with torch.no_grad():
+                    m.running_mean.mul_(1 - mom).add_(mv[0, :, 0], alpha=mom)
+                    m.running_var.mul_(1 - mom).add_(mv[0, :, 1] * (n / max(n - 1, 1)), alpha=mom)
+                    m.num_batches_tracked += 1
+
+    # -------------------------------------------------------------------------- public API
+    def forward(self, input, per_clip=False):
+        x = input.data if hasattr(input, "data") else input
+        if not x.is_cuda:
+            raise RuntimeError("phasegen UNetModel.forward needs a CUDA tensor: the B200 path has no CPU fallback")
+        if x.dim() != 3:
+            raise RuntimeError(f"expected input [B, C, T], got {tuple(x.shape)}")
+        x = x.float().contiguous()
+        B, Cn, T = x.shape
+        ex = self.executor(B, T, x.device, per_clip=per_clip)
+        if Cn != ex.levels[0].down.C_in:
+            raise RuntimeError(f"expected {ex.levels[0].down.C_in} input channels, got {Cn}")
+        ex.load_input_cf(x)
+        dn, up = self._norm_params(x.device)
+        out_cl = ex.run(dn, up)                               # [B, T, C_final] channels-last
+        if self.training and not per_clip and ex.C_final == ex.levels[0].up.C_out:
+            self._update_running_stats(ex)
+        from phasegen import ops
+        out = ops.transpose(out_cl)                           # -> [B, C_final, T]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            out = _NoBackward.apply(out, *[p for p in self.parameters() if p.requires_grad])
+        return out
+
+    def forward_channels_last(self, x_cl, per_clip=True, phase_only=True):
+        """Fused-pipeline entry: log-magnitude [B, T, C] frame-major (as the STFT kernel writes it)
+        -> channels-last output [B, T, C or 2C]; no layout change on either side."""
+        B, T, Cn = x_cl.shape
+        ex = self.executor(B, T, x_cl.device, per_clip=per_clip, phase_only=phase_only)
+        ex.load_input_cl(x_cl.contiguous())
+        dn, up = self._norm_params(x_cl.device)
+        return ex.run(dn, up)
+
+    def save(self, path):
+        torch.save({k: v.detach().cpu() for k, v in self.model.state_dict().items()}, path)
+
+    def load(self, path):
+        state_dict = torch.load(path, map_location="cpu")
+        self.model.load_state_dict(state_dict)
+        if self.gpu_ids:
+            self.model.cuda(self.gpu_ids[0])

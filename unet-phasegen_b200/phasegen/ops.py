@@ -1,0 +1,162 @@
+"""Tensor-level wrappers over the phasegen C ABI (torch is used for device memory and
+streams only; every arithmetic step below is a kernel of libphasegen.so)."""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (ActDst, ConvDesc, PG_CONV, PG_CONV_TRANSPOSE, PG_DT_BF16, PG_DT_BF16_SPLIT, PG_DT_F32,
+                   PG_DT_NONE, PG_PREC_BF16, PG_PREC_BF16X3, PG_PREC_FP32_SIMT, PG_SPEC_CARTESIAN,
+                   PG_SPEC_POLAR_LOG, PG_SPEC_POLAR_MAG, PG_STFT_LOGMAG, PG_STFT_REIM)
+
+SUPPORTED_N_FFT = (256, 512, 1024, 2048)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _need_cuda(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"phasegen: `{name}` must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"phasegen: `{name}` must be {dtype}, got {t.dtype}")
+    _lib.require_device(t.device.index)
+    return t.contiguous()
+
+
+_twiddles = {}
+
+
+def twiddle(n_fft, device):
+    """float2[n_fft] table exp(-2 pi i m / n_fft), computed in float64 on the host once."""
+    key = (n_fft, str(device))
+    if key not in _twiddles:
+        m = torch.arange(n_fft, dtype=torch.float64)
+        ang = -2.0 * math.pi * m / n_fft
+        _twiddles[key] = torch.stack([torch.cos(ang), torch.sin(ang)], 1).float().contiguous().to(device)
+    return _twiddles[key]
+
+
+def check_stft_geometry(n_fft, hop):
+    if n_fft not in SUPPORTED_N_FFT or hop * 4 != n_fft:
+        raise RuntimeError(f"phasegen: n_fft must be one of {SUPPORTED_N_FFT} with hop = n_fft/4 "
+                           f"(got n_fft={n_fft}, hop={hop})")
+
+
+def stft(wave, n_fft, hop, mode=PG_STFT_LOGMAG, want_second=True, operand=None):
+    """wave [B,N] -> (a, b) fp32 [B,T,n_fft/2] frame-major, DC bin dropped.
+    mode LOGMAG: a = log1p|X|, b = angle X;  REIM: a = Re X, b = Im X.
+    operand = (hi, lo, batch_stride): also write `a` as bf16 planes (first-conv operand)."""
+    check_stft_geometry(n_fft, hop)
+    wave = _need_cuda(wave, "wave")
+    if wave.dim() != 2:
+        raise RuntimeError("phasegen.stft: wave must be [B, N]")
+    B, N = wave.shape
+    T = 1 + N // hop
+    Cb = n_fft // 2
+    a = torch.empty(B, T, Cb, device=wave.device, dtype=torch.float32)
+    b = torch.empty_like(a) if want_second else None
+    hi, lo, bs = operand if operand is not None else (None, None, 0)
+    _lib.call("pg_stft", _ptr(wave), B, N, n_fft, hop, _ptr(twiddle(n_fft, wave.device)), mode,
+              _ptr(a), _ptr(b), _ptr(hi), _ptr(lo), bs, _stream())
+    return a, b
+
+
+def istft(a, b, mode, n_fft, hop, normalize=True, check_finite=True):
+    """(a, b) fp32 [B,T,n_fft/2] frame-major -> wave [B,(T-1)*hop]; optional peak normalisation
+    (utils.py:42) and finiteness check (utils.py:41; costs one device->host sync)."""
+    check_stft_geometry(n_fft, hop)
+    a = _need_cuda(a, "a")
+    b = _need_cuda(b, "b") if b is not None else None
+    B, T, Cb = a.shape
+    if Cb != n_fft // 2 or (b is not None and b.shape != a.shape):
+        raise RuntimeError("phasegen.istft: inputs must be [B, T, n_fft/2] and of equal shape")
+    n = (T - 1) * hop
+    wave = torch.empty(B, n, device=a.device, dtype=torch.float32)
+    peak = torch.empty(B, device=a.device, dtype=torch.float32)
+    bad = torch.empty(B, device=a.device, dtype=torch.int32)
+    _lib.call("pg_istft", _ptr(a), _ptr(b), mode, B, T, n_fft, hop, _ptr(twiddle(n_fft, a.device)),
+              _ptr(wave), _ptr(peak), _ptr(bad), _stream())
+    if normalize:
+        _lib.call("pg_peak_normalize", _ptr(wave), _ptr(peak), B, n, _stream())
+    if check_finite and bool(bad.any().item()):
+        raise ValueError("Audio buffer is not finite everywhere")
+    return wave, peak
+
+
+def transpose(src, dst=None, dst_hi=None, dst_lo=None, dst_batch_stride=None, dst_ld=None):
+    """[B,R,S] fp32 -> [B,S,R] (fp32 and/or bf16 hi/lo planes with the given pitch)."""
+    src = _need_cuda(src, "src")
+    B, R, S = src.shape
+    if dst is None and dst_hi is None:
+        dst = torch.empty(B, S, R, device=src.device, dtype=torch.float32)
+    ld = R if dst_ld is None else dst_ld
+    bs = S * ld if dst_batch_stride is None else dst_batch_stride
+    _lib.call("pg_transpose", _ptr(src), B, R, S, R * S, _ptr(dst), _ptr(dst_hi), _ptr(dst_lo), bs, ld, _stream())
+    return dst
+
+
+def conv_desc(kind, B, C_in, C_out, L_in, k, stride, pad, in_rows, in_ld, precision, L_out=None,
+              out_rows=None, out_ld=None, taps_per_group=0, base_offset_mode=0, max_ctas=0):
+    if L_out is None:
+        L_out = (L_in - 1) * stride - 2 * pad + k if kind == PG_CONV_TRANSPOSE else (L_in + 2 * pad - k) // stride + 1
+    return ConvDesc(kind, B, C_in, C_out, L_in, L_out, k, stride, pad, in_rows, in_ld,
+                    L_out if out_rows is None else out_rows, C_out if out_ld is None else out_ld,
+                    precision, taps_per_group, base_offset_mode, max_ctas)
+
+
+def pack_weight(w, kind, want_tc=True, want_simt=False):
+    """torch Conv1d [C_out,C_in,k] / ConvTranspose1d [C_in,C_out,k] weight -> kernel layouts."""
+    w = _need_cuda(w.detach(), "weight")
+    if kind == PG_CONV_TRANSPOSE:
+        C_in, C_out, k = w.shape
+    else:
+        C_out, C_in, k = w.shape
+    hi = lo = simt = None
+    if want_tc:
+        hi = torch.empty(k, C_out, C_in, device=w.device, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi)
+    if want_simt:
+        simt = torch.empty(k, C_in, C_out, device=w.device, dtype=torch.float32)
+    _lib.call("pg_pack_weight", _ptr(w), kind, C_in, C_out, k, _ptr(hi), _ptr(lo), _ptr(simt), _stream())
+    return hi, lo, simt
+
+
+def conv_tc(desc, x_hi, x_lo, w_hi, w_lo, y, stats):
+    _lib.call("pg_conv_tc", C.byref(desc), _ptr(x_hi), _ptr(x_lo), _ptr(w_hi), _ptr(w_lo), _ptr(y), _ptr(stats), _stream())
+
+
+def conv_stat_parts(desc):
+    p = _lib.load().pg_conv_stat_parts(C.byref(desc))
+    if p <= 0:
+        raise RuntimeError(f"pg_conv_stat_parts failed ({p}): {_lib.last_error()}")
+    return p
+
+
+def conv_simt(desc, x, w_simt, y):
+    _lib.call("pg_conv_simt", C.byref(desc), _ptr(x), _ptr(w_simt), _ptr(y), _stream())
+
+
+def channel_stats(y, B, L, Cn, rows, ld, stats):
+    _lib.call("pg_channel_stats", _ptr(y), B, L, Cn, rows, ld, _ptr(stats), _stream())
+
+
+def bn_finalize(stats, B, P, Cn, per_clip, gamma, beta, eps, scale_shift, mean_var=None):
+    _lib.call("pg_bn_finalize", _ptr(stats), B, P, Cn, int(per_clip), _ptr(gamma), _ptr(beta), eps,
+              _ptr(scale_shift), _ptr(mean_var), _stream())
+
+
+def act_dst(hi, lo, batch_stride, ld, ch_off, dtype, slope):
+    return ActDst(hi.data_ptr() if hi is not None else None, lo.data_ptr() if lo is not None else None,
+                  batch_stride, ld, ch_off, dtype, slope)
+
+
+def bn_act(y, B, L, Cn, rows, ld, scale_shift, per_clip, dst0, dst1=None):
+    _lib.call("pg_bn_act", _ptr(y), B, L, Cn, rows, ld, _ptr(scale_shift), int(per_clip),
+              C.byref(dst0), C.byref(dst1) if dst1 is not None else None, _stream())

@@ -1,0 +1,228 @@
+"""Executor of the U-Net forward on the phasegen kernels.
+
+Mirrors the data flow of /root/reference/model.py (UNetModel :22-43, UNetBlock :57-113) for a
+stack of D nested blocks (D = 4 in the reference), level 0 = outermost:
+
+    down conv i   : input  = raw x (i = 0) or LeakyReLU(0.2)(h_{i-1})        model.py:90,96,103
+                    h_i    = norm(z_i) for 0 < i < D-1, else z_i              (no norm outermost/innermost)
+    up conv i     : input  = ReLU(z_{D-1})                      (i = D-1)     model.py:97
+                             ReLU(cat[LeakyReLU(h_i), n_{i+1}])  (i < D-1)     model.py:91,104,113
+                             == cat[ReLU(h_i), ReLU(n_{i+1})]   (in-place LeakyReLU quirk)
+                    n_i    = norm(g_i)                                         model.py:83
+
+Every tensor is channels-last.  A convolution writes raw fp32 + statistics records; one
+bn_act launch then writes the operand(s) of the consumer(s) -- the skip concat is a write at
+a channel offset into the up-conv's input buffer, never a copy.
+"""
+import torch
+
+from . import ops
+from ._lib import (PG_CONV, PG_CONV_TRANSPOSE, PG_DT_BF16, PG_DT_BF16_SPLIT, PG_DT_F32, PG_PREC_BF16,
+                   PG_PREC_BF16X3, PG_PREC_FP32_SIMT, PRECISIONS)
+
+BN_EPS_DEFAULT = 1e-5
+# Taps that share one TMA-loaded activation strip in the tensor-core kernel (1 = no strip reuse).
+DEFAULT_TAPS_PER_GROUP = 1
+DEFAULT_BASE_OFFSET_MODE = 0
+
+
+def _rows(L):
+    """Allocated rows per clip: even (the stride-2 parity view reads row L when L is odd) and
+    padded to 8; rows >= L stay zero forever (buffers are zero-initialised, never written)."""
+    return (L + 7) // 8 * 8
+
+
+class ConvSpec:
+    def __init__(self, kind, C_in, C_out, k, stride, pad):
+        self.kind, self.C_in, self.C_out, self.k, self.stride, self.pad = kind, C_in, C_out, k, stride, pad
+
+    def out_len(self, L):
+        if self.kind == PG_CONV_TRANSPOSE:
+            return (L - 1) * self.stride - 2 * self.pad + self.k
+        return (L + 2 * self.pad - self.k) // self.stride + 1
+
+
+class LevelSpec:
+    """One UNetBlock: its down conv, optional down norm, up conv, up norm."""
+
+    def __init__(self, down, down_norm, up, up_norm=True):
+        self.down, self.down_norm, self.up, self.up_norm = down, down_norm, up, up_norm
+
+
+def tc_supported(levels):
+    return all(l.down.C_in % 64 == 0 and l.down.C_out % 128 == 0 and l.up.C_in % 64 == 0 and l.up.C_out % 128 == 0
+               for l in levels)
+
+
+class _Operand:
+    """Channels-last activation buffer [B][rows][ld]: fp32 (SIMT) or bf16 hi(/lo) planes."""
+
+    def __init__(self, B, L, ld, prec, device):
+        self.B, self.L, self.rows, self.ld = B, L, _rows(L), ld
+        if prec == PG_PREC_FP32_SIMT:
+            self.dtype = PG_DT_F32
+            self.hi = torch.zeros(B, self.rows, ld, device=device, dtype=torch.float32)
+            self.lo = None
+        else:
+            self.dtype = PG_DT_BF16_SPLIT if prec == PG_PREC_BF16X3 else PG_DT_BF16
+            self.hi = torch.zeros(B, self.rows, ld, device=device, dtype=torch.bfloat16)
+            self.lo = torch.zeros_like(self.hi) if prec == PG_PREC_BF16X3 else None
+
+    def dst(self, slope, ch_off=0):
+        return ops.act_dst(self.hi, self.lo, self.rows * self.ld, self.ld, ch_off, self.dtype, slope)
+
+    def as_float(self):
+        """Debug/test view: the stored value (hi + lo) as fp32 [B][L][ld]."""
+        v = self.hi.float()
+        if self.lo is not None:
+            v = v + self.lo.float()
+        return v[:, :self.L]
+
+
+class UNetExecutor:
+    def __init__(self, levels, B, T, device, precision="bf16x3", per_clip=False, out_channels=None,
+                 taps_per_group=None, base_offset_mode=None, keep_raw=False):
+        self.levels, self.B, self.T, self.device = levels, B, T, torch.device(device)
+        self.prec = PRECISIONS[precision] if isinstance(precision, str) else precision
+        if self.prec != PG_PREC_FP32_SIMT and not tc_supported(levels):
+            raise RuntimeError("phasegen: tensor-core path needs C_in % 64 == 0 and C_out % 128 == 0 in every "
+                               "layer; use precision='fp32_simt' for this channel count")
+        self.per_clip, self.keep_raw = per_clip, keep_raw
+        self.tpg = DEFAULT_TAPS_PER_GROUP if taps_per_group is None else taps_per_group
+        self.bo = DEFAULT_BASE_OFFSET_MODE if base_offset_mode is None else base_offset_mode
+        D = self.D = len(levels)
+        dev, prec = self.device, self.prec
+        # lengths: Ld[i] = rows entering down conv i; Ld[D] = innermost conv output
+        self.Ld = [T]
+        for lv in levels:
+            self.Ld.append(lv.down.out_len(self.Ld[-1]))
+            if self.Ld[-1] < 1:
+                raise RuntimeError(f"phasegen: time axis too short for this U-Net (T={T})")
+        for i in range(D - 1, 0, -1):
+            got, want = levels[i].up.out_len(self.Ld[i + 1]), self.Ld[i]
+            if got != want:
+                # same failure the reference hits in torch.cat (model.py:113)
+                raise RuntimeError(f"Sizes of tensors must match except in dimension 1. Expected size {want} "
+                                   f"but got size {got} for the skip connection of level {i} (T={T}; "
+                                   f"the reference U-Net needs T % 8 == 0 and T >= 24)")
+        self.T_out = levels[0].up.out_len(self.Ld[1])
+        self.C_final = levels[0].up.C_out if out_channels is None else out_channels
+        G = B if per_clip else 1
+
+        self.x0 = _Operand(B, T, levels[0].down.C_in, prec, dev)
+        self.a, self.cat, self.z, self.g = [None] * D, [None] * D, [None] * D, [None] * D
+        self.dn_desc, self.up_desc = [None] * D, [None] * D
+        self.dn_stats, self.up_stats, self.dn_ss, self.up_ss = [None] * D, [None] * D, [None] * D, [None] * D
+        self.dn_mv, self.up_mv = [None] * D, [None] * D
+        for i, lv in enumerate(levels):
+            Lz = self.Ld[i + 1]
+            src = self.x0 if i == 0 else self.a[i - 1]
+            if src.ld != lv.down.C_in:
+                raise RuntimeError(f"phasegen: level {i} down conv expects {lv.down.C_in} channels, gets {src.ld}")
+            self.a[i] = _Operand(B, Lz, lv.down.C_out, prec, dev)       # LeakyReLU(h_i)  /  ReLU(z) innermost
+            if i < D - 1:
+                self.cat[i] = _Operand(B, Lz, lv.up.C_in, prec, dev)    # [ReLU(h_i) | ReLU(n_{i+1})]
+                if lv.down.C_out + levels[i + 1].up.C_out != lv.up.C_in:
+                    raise RuntimeError(f"phasegen: level {i}: concat width {lv.down.C_out}+{levels[i + 1].up.C_out} "
+                                       f"!= up conv input {lv.up.C_in}")
+            elif lv.up.C_in != lv.down.C_out:
+                raise RuntimeError("phasegen: innermost up conv width mismatch")
+            self.dn_desc[i] = ops.conv_desc(lv.down.kind, B, lv.down.C_in, lv.down.C_out, src.L, lv.down.k,
+                                            lv.down.stride, lv.down.pad, src.rows, src.ld, prec,
+                                            taps_per_group=self.tpg, base_offset_mode=self.bo)
+            up_src = self.a[i] if i == D - 1 else self.cat[i]
+            c_out = self.C_final if i == 0 else lv.up.C_out
+            self.up_desc[i] = ops.conv_desc(lv.up.kind, B, lv.up.C_in, c_out, up_src.L, lv.up.k, lv.up.stride,
+                                            lv.up.pad, up_src.rows, up_src.ld, prec,
+                                            taps_per_group=self.tpg, base_offset_mode=self.bo)
+            self.dn_stats[i], self.dn_ss[i], self.dn_mv[i] = self._stat_bufs(self.dn_desc[i], lv.down_norm, G)
+            self.up_stats[i], self.up_ss[i], self.up_mv[i] = self._stat_bufs(self.up_desc[i], lv.up_norm, G)
+        # raw fp32 conv outputs: one shared scratch unless the caller wants to inspect them
+        sizes = [B * self.Ld[i + 1] * levels[i].down.C_out for i in range(D)] + \
+                [B * (self.T_out if i == 0 else self.Ld[i]) * self.up_desc[i].C_out for i in range(D)]
+        if keep_raw:
+            self.z = [torch.empty(s, device=dev, dtype=torch.float32) for s in sizes[:D]]
+            self.g = [torch.empty(s, device=dev, dtype=torch.float32) for s in sizes[D:]]
+        else:
+            scratch = torch.empty(max(sizes), device=dev, dtype=torch.float32)
+            self.z = [scratch] * D
+            self.g = [scratch] * D
+        self.out = torch.empty(B, self.T_out, self.C_final, device=dev, dtype=torch.float32)
+
+    def _stat_bufs(self, desc, has_norm, G):
+        if not has_norm:
+            return None, None, None
+        P = ops.conv_stat_parts(desc) if self.prec != PG_PREC_FP32_SIMT else 1
+        stats = torch.empty(self.B, P, desc.C_out, 4, device=self.device, dtype=torch.float32)
+        ss = torch.empty(G, desc.C_out, 2, device=self.device, dtype=torch.float32)
+        mv = torch.empty(G, desc.C_out, 2, device=self.device, dtype=torch.float32)
+        return stats, ss, mv
+
+    # ------------------------------------------------------------------------------ weights
+    def pack_weights(self, down_w, up_w):
+        """down_w/up_w: per level, the torch-layout weights.  The final up conv is sliced to
+        the first C_final output channels (phase-only inference)."""
+        tc = self.prec != PG_PREC_FP32_SIMT
+        self.wd, self.wu = [], []
+        for i, lv in enumerate(self.levels):
+            self.wd.append(ops.pack_weight(down_w[i], lv.down.kind, want_tc=tc, want_simt=not tc))
+            w = up_w[i]
+            if i == 0 and self.C_final != lv.up.C_out:
+                w = w[:, :self.C_final].contiguous()
+            self.wu.append(ops.pack_weight(w, lv.up.kind, want_tc=tc, want_simt=not tc))
+
+    # ------------------------------------------------------------------------------ forward
+    def _conv(self, desc, src, w, y, stats):
+        if self.prec == PG_PREC_FP32_SIMT:
+            ops.conv_simt(desc, src.hi, w[2], y)
+            if stats is not None:
+                ops.channel_stats(y, desc.B, desc.L_out, desc.C_out, desc.out_rows, desc.out_ld, stats)
+        else:
+            ops.conv_tc(desc, src.hi, src.lo, w[0], w[1], y, stats)
+
+    def _norm_act(self, desc, y, stats, ss, mv, gamma, beta, eps, dst0, dst1=None):
+        P = 1
+        if stats is not None:
+            P = stats.shape[1]
+            ops.bn_finalize(stats, desc.B, P, desc.C_out, self.per_clip, gamma, beta, eps, ss, mv)
+        ops.bn_act(y, desc.B, desc.L_out, desc.C_out, desc.out_rows, desc.out_ld,
+                   ss if stats is not None else None, self.per_clip, dst0, dst1)
+
+    def load_input_cf(self, x):
+        """x [B,C,T] fp32 (reference layout) -> the level-0 operand (one transposing kernel)."""
+        B, Cn, T = x.shape
+        ops.transpose(x, dst=self.x0.hi if self.x0.dtype == PG_DT_F32 else None,
+                      dst_hi=None if self.x0.dtype == PG_DT_F32 else self.x0.hi, dst_lo=self.x0.lo,
+                      dst_batch_stride=self.x0.rows * self.x0.ld, dst_ld=self.x0.ld)
+
+    def load_input_cl(self, x_cl):
+        """x [B,T,C] fp32 channels-last -> level-0 operand (identity bn_act = cast/split)."""
+        B, T, Cn = x_cl.shape
+        ops.bn_act(x_cl, B, T, Cn, T, Cn, None, False, self.x0.dst(1.0))
+
+    def run(self, dn_norm, up_norm):
+        """dn_norm/up_norm: per level (gamma, beta, eps) or None.  Consumes self.x0; returns
+        the channels-last output [B][T_out][C_final] (a persistent buffer of the executor)."""
+        D, lv = self.D, self.levels
+        for i in range(D):
+            src = self.x0 if i == 0 else self.a[i - 1]
+            self._conv(self.dn_desc[i], src, self.wd[i], self.z[i], self.dn_stats[i])
+            gam, bet, eps = dn_norm[i] if lv[i].down_norm else (None, None, BN_EPS_DEFAULT)
+            if i < D - 1:
+                self._norm_act(self.dn_desc[i], self.z[i], self.dn_stats[i], self.dn_ss[i], self.dn_mv[i], gam, bet, eps,
+                               self.a[i].dst(0.2), self.cat[i].dst(0.0, 0))
+            else:
+                self._norm_act(self.dn_desc[i], self.z[i], self.dn_stats[i], self.dn_ss[i], self.dn_mv[i], gam, bet, eps,
+                               self.a[i].dst(0.0))
+        for i in range(D - 1, -1, -1):
+            src = self.a[i] if i == D - 1 else self.cat[i]
+            self._conv(self.up_desc[i], src, self.wu[i], self.g[i], self.up_stats[i])
+            gam, bet, eps = up_norm[i] if lv[i].up_norm else (None, None, BN_EPS_DEFAULT)
+            if i == 0 and gam is not None and self.C_final != lv[0].up.C_out:
+                gam, bet = gam[:self.C_final], bet[:self.C_final]
+            if i > 0:
+                dst = self.cat[i - 1].dst(0.0, lv[i - 1].down.C_out)
+            else:
+                dst = ops.act_dst(self.out, None, self.T_out * self.C_final, self.C_final, 0, PG_DT_F32, 1.0)
+            self._norm_act(self.up_desc[i], self.g[i], self.up_stats[i], self.up_ss[i], self.up_mv[i], gam, bet, eps, dst)
+        return self.out
