@@ -33,9 +33,7 @@ def _case(layer, C, L_in, B, seed=0):
 @pytest.mark.parametrize("C,scale", [(8, 1), (16, 3)])
 def test_simt_conv_matches_torch(layer, C, scale):
     from phasegen import ops
-    L_in, B = LENS[layer] * scale // (2 if scale > 1 and layer == "d1" else 1), 2
-    if layer == "d1":
-        L_in = 136 if scale == 1 else 200
+    L_in, B = LENS[layer] * scale + (scale - 1), 2
     kind, k, s, p, C_in, C_out, rows, x, w = _case(layer, C, L_in, B)
     d = ops.conv_desc(kind, B, C_in, C_out, L_in, k, s, p, rows, C_in, ops.PG_PREC_FP32_SIMT)
     _, _, ws = ops.pack_weight(w, kind, want_tc=False, want_simt=True)
