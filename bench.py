@@ -1,0 +1,286 @@
+"""Benchmark of the magnitude -> phase -> waveform hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (configs[1] of BASELINE.json): 256 synthetic 4 s / 44.1 kHz mono clips per GPU,
+n_fft 1024, hop 256 (T = 696 frames after padding to a multiple of 8, N = 177,920 samples),
+STFT -> U-Net (C = 512, random-init weights, per-clip train-mode norm statistics = the
+demo.py batch-1 loop) -> ISTFT with peak normalisation.  One "step" = one pass over the
+batch.  metric = audio-seconds processed per wall second, whole job (all ranks).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "unet-phasegen_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SR, N_FFT, HOP, SECONDS = 44100, 1024, 256, 4.0
+CLIPS_PER_GPU = 256
+METRIC = "audio_seconds_per_second_mag_to_phase_to_wave"
+UNIT = "audio-s/s"
+
+
+def workload_geometry():
+    from phasegen import synth
+    T = synth.frames_for(SECONDS, SR, HOP)
+    N = (T - 1) * HOP
+    return T, N, N / SR
+
+
+def unet_flops_per_clip(C, T, phase_only):
+    """Algorithmic MACs*2 of the eight convolutions, per clip."""
+    L1 = T // 2 + 1; L2 = L1 - 3; L3 = L2 // 2 - 2; L4 = (L3 - 1) // 2
+    c2, c4 = 2 * C, 4 * C
+    per_layer = {
+        "d1": C * c2 * 32 * L1, "d2": c2 * c2 * 8 * L2, "d3": c2 * c2 * 8 * L3, "d4": c2 * c4 * 4 * L4,
+        "u4": c4 * c2 * 5 * L4, "u3": c4 * c2 * 8 * L3, "u2": c4 * c2 * 8 * L2,
+        "u1": c4 * (C if phase_only else c2) * 32 * L1,
+    }
+    return {k: 2 * v for k, v in per_layer.items()}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_step(n_clips, seed=0, time_budget_s=None):
+    """The reference's CPU path (oracle port: numpy STFT/ISTFT restating librosa + the reference
+    U-Net arithmetic through torch CPU fp32 with oneDNN off, batch 1 per clip like demo.py:33-42)
+    on `n_clips` clips of the bench workload.  Returns (seconds, clips done)."""
+    import numpy as np
+    import torch
+    from oracle import stft_np, unet_torch
+    from phasegen import synth
+    T, N, _ = workload_geometry()
+    C = N_FFT // 2
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = unet_torch.random_state_dict(C, seed=seed)
+    waves = synth.synthetic_waves(n_clips, N, SR, seed=seed).numpy()
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(n_clips):
+        S = stft_np.stft(waves[i], N_FFT, HOP)[1:]
+        lm = np.log1p(np.abs(S)).astype(np.float32)
+        out = unet_torch.unet_forward(sd, torch.from_numpy(lm)[None], torch.float32, per_clip_bn=True)[0].numpy()
+        stft_np.generate_audio(stft_np.polar_to_complex(lm, out[:C]), SR, HOP, is_stft=True)
+        done += 1
+        if time_budget_s is not None and time.perf_counter() - t0 > time_budget_s:
+            break
+    return time.perf_counter() - t0, done
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    T, N, clip_s = workload_geometry()
+    cores = os.cpu_count() or 1
+    n = 2
+    for _ in range(args.warmup):
+        cpu_reference_step(1)
+    times = []
+    for _ in range(args.steps):
+        dt, done = cpu_reference_step(n)
+        times.append(dt / done)
+    per_clip = statistics.mean(times)
+    value = clip_s / per_clip
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_clip * n * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{n} clips/step of the batched-inference workload (4 s @ 44.1 kHz, n_fft {N_FFT}, hop {HOP}, "
+                                   f"T {T}, C {N_FFT // 2}), batch-1 per clip like demo.py",
+                       "timing": "host perf_counter; CPU only"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n} clips per step x {args.steps} steps, oracle port (numpy STFT/ISTFT + torch-CPU fp32 U-Net, oneDNN off)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="phasegen", choices=["phasegen", "reference"])
+    ap.add_argument("--clips", type=int, default=CLIPS_PER_GPU, help="clips per GPU per step")
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32_simt"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import model as pg_model
+    from phasegen import _lib, synth
+    from phasegen.pipeline import PhaseGenPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the phasegen path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+
+    T, N, clip_s = workload_geometry()
+    C, B = N_FFT // 2, args.clips
+    torch.manual_seed(1234)
+    net = pg_model.UNetModel(C, 2 * C).to(dev)
+    synth.randomize_norm_affine(net, seed=7)
+    pipe = PhaseGenPipeline(net, N_FFT, HOP, precision=args.precision, per_clip=True, phase_only=True, normalize=True)
+    host_in = synth.synthetic_waves(B, N, SR, seed=100 + rank).pin_memory()
+    host_out = torch.empty(B, N, dtype=torch.float32).pin_memory()
+    wave = host_in.to(dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident():
+        return pipe(wave)
+
+    def step_e2e():
+        d = host_in.to(dev, non_blocking=True)
+        out = pipe(d)
+        host_out.copy_(out, non_blocking=True)
+
+    for _ in range(W):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launches
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    audio_s = world * B * clip_s
+    value = audio_s / (ms / args.steps / 1e3)
+    e2e = audio_s / (ms_e2e / args.steps / 1e3)
+
+    # ---- roofline of the dominant kernel (conv_tc_kernel): CUDA events around every launch
+    from phasegen import ops
+    conv_ms = {"n": 0, "ms": 0.0}
+    pending = []
+    orig = ops.conv_tc
+
+    def conv_timed(desc, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); orig(desc, *a); e1.record()
+        pending.append((e0, e1))
+    roof = None
+    if args.precision != "fp32_simt":
+        ops.conv_tc = conv_timed
+        import phasegen.unet as _u
+        for _ in range(args.steps):
+            step_resident()
+        torch.cuda.synchronize()
+        ops.conv_tc = orig
+        tot_ms = sum(a.elapsed_time(b) for a, b in pending)
+        n_launch = len(pending)
+        flops_step = sum(unet_flops_per_clip(C, T, True).values()) * B
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = peaks.get("bf16_tflops_sustained", 1590.0 if not peaks else None) or 1590.0
+        achieved = flops_step * args.steps / (tot_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "launches": n_launch, "avg_launch_ms": tot_ms / max(n_launch, 1),
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                "note": "algorithmic FLOPs (8 convs, phase-only last layer); the fp32-class mode issues 3 bf16 MMAs per "
+                        "algorithmic MAC, so tensor-pipe work is 3x this figure",
+                "conv_share_of_step": (tot_ms / args.steps) / (ms / args.steps)}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        dt, done = cpu_reference_step(16, time_budget_s=12.0)
+        cpu = {"value": clip_s * done / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"{done} clips of the same workload, batch-1 per clip (demo.py loop), numpy STFT/ISTFT + torch-CPU fp32 U-Net (oneDNN off)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"bf16x3": "bf16x3-fp32acc", "bf16": "bf16-fp32acc", "fp32_simt": "f32"}[args.precision],
+                "data": "synthetic",
+                "config": {"workload": f"batched inference: {B} clips/GPU x 4 s @ 44.1 kHz (N {N}), n_fft {N_FFT}, hop {HOP}, "
+                                       f"T {T}, U-Net C {C} (153 M params, random init), STFT->U-Net->ISTFT+peak-normalise",
+                           "norm_statistics": "per clip (demo.py batch-1 semantics)", "last_layer": "phase-only",
+                           "l2_policy": f"inputs larger than L2 ({B * N * 4 / 1e6:.0f} MB wave, >2 GB of activations per step)",
+                           "timing": "CUDA events on the launch stream, max over ranks"},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * N * 4, "d2h_bytes_per_step": B * N * 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -16,7 +16,9 @@ GEOMS = [(256, 64), (512, 128), (1024, 256), (2048, 512)]
 
 
 def rel_l2(a, b):
-    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    a = np.asarray(a); b = np.asarray(b)
+    dt = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    a = a.astype(dt); b = b.astype(dt)
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
 
 

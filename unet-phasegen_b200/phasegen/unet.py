@@ -22,7 +22,9 @@ from ._lib import (PG_CONV, PG_CONV_TRANSPOSE, PG_DT_BF16, PG_DT_BF16_SPLIT, PG_
 
 BN_EPS_DEFAULT = 1e-5
 # Taps that share one TMA-loaded activation strip in the tensor-core kernel (1 = no strip reuse).
-DEFAULT_TAPS_PER_GROUP = 1
+# 16 with base-offset mode 0 verified on B200 against the SIMT kernel (tools/tc_probe.py,
+# profiles/r01_tc_probe.log): the UMMA swizzle is a function of the absolute smem address.
+DEFAULT_TAPS_PER_GROUP = 16
 DEFAULT_BASE_OFFSET_MODE = 0
 
 
