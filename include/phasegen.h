@@ -76,6 +76,7 @@ typedef struct pg_conv_desc {
     int taps_per_group;       /* tensor-core path: taps sharing one activation strip (0 = default 16, 1 = off) */
     int tc_base_offset_mode;  /* tensor-core path: descriptor base-offset handling of shifted strips */
     int tc_max_ctas;          /* tensor-core path: cap on the persistent grid (0 = one per SM) */
+    int max_clips_per_tile;   /* tensor-core path: clips packed into one tile for short time axes (0 = auto, 1 = off) */
 } pg_conv_desc;
 
 /* weights: torch layout (Conv1d [C_out][C_in][k], ConvTranspose1d [C_in][C_out][k])

@@ -93,6 +93,29 @@ def test_tc_conv_full_width_tiles_and_persistence():
         assert float((y - ys).norm() / ys.norm()) < 3e-5, layer
 
 
+def test_tc_conv_clip_groups_and_clip_bundles(monkeypatch):
+    """Tile-order groups (forced small through the PG_TC_CLIP_GROUP test hook) and several clips
+    per tile (short time axes), with a batch that is not a multiple of the bundle size."""
+    from phasegen import ops
+    monkeypatch.setenv("PG_TC_CLIP_GROUP", "2")
+    for layer, C, L_in, B in (("d4", 128, 171, 7), ("u4", 128, 85, 7), ("d2", 64, 69, 11), ("u1", 64, 69, 5), ("d3", 64, 30, 19)):
+        kind, k, s, p, C_in, C_out, rows, x, w = _case(layer, C, L_in, B, seed=3)
+        d = ops.conv_desc(kind, B, C_in, C_out, L_in, k, s, p, rows, C_in, ops.PG_PREC_BF16X3, taps_per_group=16)
+        ds = ops.conv_desc(kind, B, C_in, C_out, L_in, k, s, p, rows, C_in, ops.PG_PREC_FP32_SIMT)
+        hi, lo, ws = ops.pack_weight(w, kind, True, True)
+        xh = x.to(torch.bfloat16); xl = (x - xh.float()).to(torch.bfloat16)
+        y = torch.full((B, d.L_out, C_out), float("nan"), device="cuda")
+        ys = torch.empty_like(y)
+        P = ops.conv_stat_parts(d)
+        st = torch.zeros(B, P, C_out, 4, device="cuda")
+        ops.conv_tc(d, xh, xl, hi, lo, y, st)
+        ops.conv_simt(ds, x, ws, ys)
+        torch.cuda.synchronize()
+        assert not torch.isnan(y).any(), layer
+        assert float((y - ys).norm() / ys.norm()) < 3e-5, layer
+        assert bool((st[..., 0].sum(1) == d.L_out).all()), layer
+
+
 def test_conv_argument_errors():
     from phasegen import ops
     x = torch.zeros(1, 32, 48, device="cuda", dtype=torch.bfloat16)

@@ -44,3 +44,56 @@ def test_pipeline_matches_oracle_chain(n_fft, T, prec):
         got = audio[b].cpu().numpy()
         assert rel_l2(got, ref) < 5e-3
         assert abs(snr_db(w, got) - snr_db(w, ref)) < 0.1
+
+
+def test_long_form_windows_match_pipeline_and_seams_sum_to_one():
+    """Config 4 (long-form): every window equals the plain pipeline on that window, the seam
+    weights sum to one (a constant signal stitches back to itself), ranks partition the windows."""
+    import model
+    from phasegen import longform, synth
+    from phasegen.pipeline import PhaseGenPipeline
+    n_fft, hop, frames = 256, 64, 40
+    C = n_fft // 2
+    torch.manual_seed(3)
+    net = model.UNetModel(C, 2 * C).cuda()
+    pipe = PhaseGenPipeline(net, n_fft, hop, per_clip=True, phase_only=True, normalize=False)
+    N = 5 * (frames - 1) * hop // 2 + 777                        # ragged: last window is zero-padded
+    wave = synth.synthetic_waves(1, N, sr=16000, seed=4, device="cuda")[0]
+    win, step, n = longform.window_plan(N, hop, frames)
+    assert step == (win // 2) // hop * hop and win + (n - 1) * step >= N
+    wins, idx = longform.cut_windows(wave, hop, frames)
+    assert wins.shape == (n, win) and idx == list(range(n))
+    parts = [longform.cut_windows(wave, hop, frames, r, 3) for r in range(3)]
+    assert sorted(i for _, ix in parts for i in ix) == list(range(n))
+    ones = longform.stitch(torch.ones(n, win, device="cuda"), idx, n, N, hop, frames)
+    assert float((ones - 1).abs().max()) < 1e-6
+    y = longform.process_long(pipe, wave, frames=frames, batch=4, peak_normalize=False)
+    per_window = pipe(wins).clone()
+    ref = longform.stitch(per_window, idx, n, N, hop, frames)
+    assert y.shape == (N,) and torch.allclose(y, ref, atol=1e-6)
+    single = pipe(wins[2:3].contiguous())
+    assert float((single[0] - per_window[2]).abs().max()) < 1e-5 * float(per_window[2].abs().max()) + 1e-7
+
+
+@pytest.mark.parametrize("n_fft,T", [(512, 1384), (1024, 696), (2048, 352)])
+def test_shape_sweep_full_path_one_clip(n_fft, T):
+    """Config 5 shapes (n_fft 512 / hop 128 / T 1384 and n_fft 2048 / hop 512 / T 352) through the
+    whole path at batch 1, against the oracle chain."""
+    import model
+    from phasegen import synth
+    from phasegen.pipeline import PhaseGenPipeline
+    hop, C = n_fft // 4, n_fft // 2
+    torch.manual_seed(5)
+    net = model.UNetModel(C, 2 * C).cuda()
+    synth.randomize_norm_affine(net, seed=6)
+    sd = {k: v.detach().cpu() for k, v in net.model.state_dict().items()}
+    wave = synth.synthetic_waves(1, (T - 1) * hop, sr=44100, seed=7, device="cuda")
+    pipe = PhaseGenPipeline(net, n_fft, hop, per_clip=True, phase_only=True)
+    audio, logmag, phase = pipe(wave, check_finite=True, return_intermediates=True)
+    w = wave[0].cpu().numpy().astype(np.float64)
+    lm = np.log1p(np.abs(stft_np.stft(w, n_fft, hop)[1:]))
+    out = unet_torch.unet_forward(sd, torch.from_numpy(lm)[None], torch.float64, per_clip_bn=True)[0].numpy()
+    ref = stft_np.generate_audio(stft_np.polar_to_complex(lm, out[:C]), 44100, hop, is_stft=True)
+    assert rel_l2(logmag[0].cpu().numpy().T, lm) < 1e-4
+    assert rel_l2(phase[0].cpu().numpy().T, out[:C]) < 1e-3
+    assert abs(snr_db(w, audio[0].cpu().numpy()) - snr_db(w, ref)) < 0.1

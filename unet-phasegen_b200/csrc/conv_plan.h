@@ -25,6 +25,8 @@ struct ConvPlan {
     int n_tile, n_ntiles;       // positions per tile (multiple of 16, <= 256), tiles per phase
     int n_chunks, n_cotiles;    // C_in / 64, C_out / 128
     int strip_rows;             // rows of one activation strip (n_tile + largest shift, rounded to 8)
+    int nb;                     // clips per tile: short time axes pack several clips into one 128 x (nb*n_tile) tile
+    int clip_group;             // tensor-core tile order: clips per L2-resident group (set by the launcher)
     int out_rows, out_ld;
     int n_groups[2], n_taps[2];
     ConvGroup groups[2][kMaxTaps];
@@ -91,6 +93,19 @@ static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
     }
     p->strip_rows = (p->n_tile + max_shift + 7) / 8 * 8;
     if (p->strip_rows > 256) p->strip_rows = 256;
+    // Several clips per tile when one clip's positions leave the 256-column accumulator mostly
+    // empty: the weight tile is then shared by nb MMAs (one per clip).
+    p->nb = 1;
+    if (p->n_ntiles == 1 && d->max_clips_per_tile != 1) {
+        int nb = 256 / p->n_tile;
+        if (nb > 256 / p->strip_rows) nb = 256 / p->strip_rows;
+        if (nb > 8) nb = 8;
+        if (d->max_clips_per_tile > 1 && nb > d->max_clips_per_tile) nb = d->max_clips_per_tile;
+        if (nb > d->B) nb = d->B;
+        if (nb < 1) nb = 1;
+        p->nb = nb;
+    }
+    p->clip_group = d->B;
     return PG_OK;
 }
 

@@ -28,6 +28,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "conv_plan.h"
@@ -61,6 +62,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const long long t0 = clock64();
     for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins) {
         if ((spins & 1023u) == 0 && clock64() - t0 > 4000000000ll) {   // ~2 s at 1.9 GHz
+            printf("phasegen conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n",
+                   (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
+    }
+}
+// Long waits (epilogue warps idle for a whole K loop): back off instead of burning issue slots.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins) {
+        __nanosleep(ns);
+        if ((spins & 255u) == 0 && clock64() - t0 > 4000000000ll) {
             printf("phasegen conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n",
                    (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
             __trap();
@@ -148,14 +162,23 @@ constexpr int kThreads = 192;
 constexpr int kATileBytes = 128 * 128;        // one plane: 128 co x 64 ci bf16
 constexpr int kMaxASlots = 6;
 
-struct TileCoord { int co_tile, phase, b, nt; };
+struct TileCoord { int co_tile, phase, b0, nt; };
 
+// Tile order: clips are taken in L2-sized groups; inside a group all tiles of one weight slab
+// (128 output channels x one output phase) are adjacent, so co-resident CTAs share the slab and
+// the group's activations are read from HBM once and re-used from L2 by every slab.
+__device__ __forceinline__ int n_bundles(const ConvPlan& p) { return (p.B + p.nb - 1) / p.nb; }
+__device__ __forceinline__ int total_tiles(const ConvPlan& p) { return p.n_cotiles * p.OS * n_bundles(p) * p.n_ntiles; }
 __device__ __forceinline__ TileCoord decode_tile(const ConvPlan& p, int tile) {
     TileCoord c;
-    int per_slab = p.B * p.n_ntiles;
-    int slab = tile / per_slab, r = tile % per_slab;
+    const int nbg = n_bundles(p), G = p.clip_group, n_slabs = p.n_cotiles * p.OS;
+    const int tiles_full = n_slabs * G * p.n_ntiles;
+    const int g = tile / tiles_full, r = tile % tiles_full;
+    int Gg = nbg - g * G; if (Gg > G) Gg = G;
+    const int per_slab = Gg * p.n_ntiles;
+    const int slab = r / per_slab, r2 = r % per_slab;
     c.co_tile = slab / p.OS; c.phase = slab % p.OS;
-    c.b = r / p.n_ntiles; c.nt = r % p.n_ntiles;
+    c.b0 = (g * G + r2 / p.n_ntiles) * p.nb; c.nt = r2 % p.n_ntiles;
     return c;
 }
 
@@ -180,7 +203,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accEmpty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = pl.n_cotiles * pl.OS * pl.B * pl.n_ntiles;
+    const int n_tiles = total_tiles(pl);
     const bool three = prm.n_terms == 3;
 
     if (warp == 0 && lane == 0) {
@@ -217,8 +240,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                             mbar_wait(emptyB + s, ph ^ 1);
                             mbar_expect_tx(fullB + s, b_bytes);
                             uint8_t* dst = b_base + (size_t)s * 2 * bPlane;
-                            tma_load_4d(dst, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b);
-                            if (three) tma_load_4d(dst + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b);
+                            tma_load_4d(dst, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
+                            if (three) tma_load_4d(dst + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
                             ++b_it;
                         }
                         for (int j = 0; j < grp.n_taps; ++j) {
@@ -243,11 +266,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_it) {
                 TileCoord tc = decode_tile(pl, tile);
                 const int acc = t_it & 1; const uint32_t acc_ph = (t_it >> 1) & 1;
-                mbar_wait(accEmpty + acc, acc_ph ^ 1);
+                mbar_wait_sleep(accEmpty + acc, acc_ph ^ 1, 200);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 const int ng = pl.n_groups[tc.phase];
-                uint32_t accumulate = 0;
+                uint32_t accumulate = 0, accumulate_rest = 0;
+                const uint32_t clip_bytes = (uint32_t)pl.strip_rows * 128u;
                 for (int ch = 0; ch < pl.n_chunks; ++ch) {
                     for (int g = 0; g < ng; ++g) {
                         const ConvGroup grp = pl.groups[tc.phase][g];
@@ -264,21 +288,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                             const uint32_t a_hi = smem_u32(a_base + (size_t)as * 2 * kATileBytes);
                             const uint32_t a_lo = a_hi + kATileBytes;
                             const uint32_t sh = (uint32_t)tp.shift * 128u;
+                            for (int c = 0; c < pl.nb; ++c) {      // one MMA group per clip of the bundle
+                                const uint32_t boff = (uint32_t)c * clip_bytes + sh;
+                                const uint32_t dcol = d_tmem + c * pl.n_tile;
+                                const uint32_t acc_c = c == 0 ? accumulate : accumulate_rest;
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {       // 4 x (K = 16) per 64-channel chunk
-                                const uint64_t da_hi = make_desc_sw128(a_hi + kk * 32, 0);
-                                const uint64_t db_hi = make_desc_sw128(b_hi + sh + kk * 32, prm.base_offset_mode);
-                                if (three) {
-                                    const uint64_t da_lo = make_desc_sw128(a_lo + kk * 32, 0);
-                                    const uint64_t db_lo = make_desc_sw128(b_lo + sh + kk * 32, prm.base_offset_mode);
-                                    umma_bf16(d_tmem, da_lo, db_hi, idesc, accumulate);
-                                    umma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
-                                    umma_bf16(d_tmem, da_hi, db_hi, idesc, 1);
-                                } else {
-                                    umma_bf16(d_tmem, da_hi, db_hi, idesc, accumulate);
+                                for (int kk = 0; kk < 4; ++kk) {   // 4 x (K = 16) per 64-channel chunk
+                                    const uint64_t da_hi = make_desc_sw128(a_hi + kk * 32, 0);
+                                    const uint64_t db_hi = make_desc_sw128(b_hi + boff + kk * 32, prm.base_offset_mode);
+                                    if (three) {
+                                        const uint64_t da_lo = make_desc_sw128(a_lo + kk * 32, 0);
+                                        const uint64_t db_lo = make_desc_sw128(b_lo + boff + kk * 32, prm.base_offset_mode);
+                                        umma_bf16(dcol, da_lo, db_hi, idesc, kk == 0 ? acc_c : 1u);
+                                        umma_bf16(dcol, da_hi, db_lo, idesc, 1);
+                                        umma_bf16(dcol, da_hi, db_hi, idesc, 1);
+                                    } else {
+                                        umma_bf16(dcol, da_hi, db_hi, idesc, kk == 0 ? acc_c : 1u);
+                                    }
                                 }
-                                accumulate = 1;
                             }
+                            accumulate = 1; accumulate_rest = 1;
                             umma_commit(emptyA + as);
                             ++a_it;
                         }
@@ -299,39 +328,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
             const int m0 = tc.nt * pl.n_tile;
             const int l_phase = (pl.L_out - tc.phase + pl.OS - 1) / pl.OS;   // positions of this phase
             int n_valid = l_phase - m0; if (n_valid > pl.n_tile) n_valid = pl.n_tile; if (n_valid < 0) n_valid = 0;
-            mbar_wait(accFull + acc, acc_ph);
+            mbar_wait_sleep(accFull + acc, acc_ph, 1000);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
             const int co = tc.co_tile * 128 + q * 32 + lane;
-            // pass 1: mean over the valid columns
-            float sum = 0.f;
-            for (int c0 = 0; c0 < n_valid; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + c0, v);
+            for (int c = 0; c < pl.nb; ++c) {
+                const int b = tc.b0 + c;
+                if (b >= pl.B) break;
+                const uint32_t taddr = tmem_base + acc * 256 + c * pl.n_tile + ((uint32_t)(q * 32) << 16);
+                // pass 1: mean over the valid columns
+                float sum = 0.f;
+                for (int c0 = 0; c0 < n_valid; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + c0, v);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) if (c0 + i < n_valid) sum += v[i];
-            }
-            const float mean = n_valid > 0 ? sum / (float)n_valid : 0.f;
-            // pass 2: centred second moment + store
-            float m2 = 0.f;
-            float* yrow = prm.y + ((size_t)tc.b * pl.out_rows) * pl.out_ld + co;
-            for (int c0 = 0; c0 < n_valid; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + c0, v);
+                    for (int i = 0; i < 16; ++i) if (c0 + i < n_valid) sum += v[i];
+                }
+                const float mean = n_valid > 0 ? sum / (float)n_valid : 0.f;
+                // pass 2: centred second moment + store
+                float m2 = 0.f;
+                float* yrow = prm.y + ((size_t)b * pl.out_rows) * pl.out_ld + co;
+                for (int c0 = 0; c0 < n_valid; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + c0, v);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (c0 + i < n_valid) {
-                        float d = v[i] - mean;
-                        m2 += d * d;
-                        const int row = (m0 + c0 + i) * pl.OS + tc.phase;
-                        yrow[(size_t)row * pl.out_ld] = v[i];
+                    for (int i = 0; i < 16; ++i) {
+                        if (c0 + i < n_valid) {
+                            float d = v[i] - mean;
+                            m2 += d * d;
+                            const int row = (m0 + c0 + i) * pl.OS + tc.phase;
+                            yrow[(size_t)row * pl.out_ld] = v[i];
+                        }
                     }
                 }
-            }
-            if (prm.stats) {
-                const int P = pl.OS * pl.n_ntiles;
-                const int p = tc.phase * pl.n_ntiles + tc.nt;
-                prm.stats[((size_t)tc.b * P + p) * pl.C_out + co] = make_float4((float)n_valid, mean, m2, 0.f);
+                if (prm.stats) {
+                    const int P = pl.OS * pl.n_ntiles;
+                    const int p = tc.phase * pl.n_ntiles + tc.nt;
+                    prm.stats[((size_t)b * P + p) * pl.C_out + co] = make_float4((float)n_valid, mean, m2, 0.f);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -399,7 +432,7 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     prm.y = y; prm.stats = reinterpret_cast<float4*>(stats);
     prm.n_terms = three ? 3 : 1;
     prm.base_offset_mode = d->tc_base_offset_mode;
-    prm.b_slot_bytes = pl.strip_rows * 128;
+    prm.b_slot_bytes = pl.nb * pl.strip_rows * 128;
     const int fixed = 4 * prm.b_slot_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
     int nA = (g_max_smem - fixed) / (2 * kATileBytes);
     if (nA > kMaxASlots) nA = kMaxASlots;
@@ -421,7 +454,7 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
         const int IS = pl.IS;
         uint64_t dims[4] = {(uint64_t)d->C_in, (uint64_t)IS, (uint64_t)((d->L_in + IS - 1) / IS), (uint64_t)d->B};
         uint64_t str[3] = {(uint64_t)d->in_ld * 2, (uint64_t)d->in_ld * 2 * IS, (uint64_t)d->in_rows * d->in_ld * 2};
-        uint32_t box[4] = {64, 1, (uint32_t)pl.strip_rows, 1};
+        uint32_t box[4] = {64, 1, (uint32_t)pl.strip_rows, (uint32_t)pl.nb};
         PG_REQUIRE(d->in_rows >= ((d->L_in + IS - 1) / IS) * IS, "pg_conv_tc: in_rows %d too small for L_in %d at stride %d", d->in_rows, d->L_in, IS);
         if ((rc = encode_bf16(&mx_hi, x_hi, 4, dims, str, box, "x_hi")) != PG_OK) return rc;
         if ((rc = encode_bf16(&mx_lo, three ? x_lo : x_hi, 4, dims, str, box, "x_lo")) != PG_OK) return rc;
@@ -432,7 +465,17 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
         if (e != cudaSuccess) { set_error("conv_tc: cannot opt in to %zu bytes of shared memory: %s", smem_bytes, cudaGetErrorString(e)); return PG_ERR_CUDA; }
         configured = smem_bytes;
     }
-    const int n_tiles = pl.n_cotiles * pl.OS * pl.B * pl.n_ntiles;
+    {
+        // clips per L2-resident group: keep ~64 MB of activations hot while every weight slab passes over them
+        const int nbg = (pl.B + pl.nb - 1) / pl.nb;
+        const double bundle_bytes = (double)pl.nb * d->in_rows * d->in_ld * (three ? 4.0 : 2.0);
+        int G = (int)(64.0e6 / bundle_bytes);
+        if (const char* e = getenv("PG_TC_CLIP_GROUP")) G = atoi(e);   // test hook: force small groups
+        if (G < 1) G = 1;
+        if (G > nbg) G = nbg;
+        prm.plan.clip_group = G;
+    }
+    const int n_tiles = pl.n_cotiles * pl.OS * ((pl.B + pl.nb - 1) / pl.nb) * pl.n_ntiles;
     int grid = n_tiles < g_sm_count ? n_tiles : g_sm_count;
     if (d->tc_max_ctas > 0 && grid > d->tc_max_ctas) grid = d->tc_max_ctas;
     conv_tc_kernel<<<grid, kThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(mw_hi, mw_lo, mx_hi, mx_lo, prm);
