@@ -60,7 +60,7 @@ def test_long_form_windows_match_pipeline_and_seams_sum_to_one():
     N = 5 * (frames - 1) * hop // 2 + 777                        # ragged: last window is zero-padded
     wave = synth.synthetic_waves(1, N, sr=16000, seed=4, device="cuda")[0]
     win, step, n = longform.window_plan(N, hop, frames)
-    assert step == (win // 2) // hop * hop and win + (n - 1) * step >= N
+    assert step % hop == 0 and 2 * step >= win and win + (n - 1) * step >= N
     wins, idx = longform.cut_windows(wave, hop, frames)
     assert wins.shape == (n, win) and idx == list(range(n))
     parts = [longform.cut_windows(wave, hop, frames, r, 3) for r in range(3)]

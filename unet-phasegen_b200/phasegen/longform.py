@@ -20,7 +20,7 @@ import torch
 def window_plan(n_samples, hop, frames=696):
     """(window length in samples, step between windows, number of windows)."""
     win = (frames - 1) * hop
-    step = (win // 2) // hop * hop
+    step = -(-(win // 2) // hop) * hop          # >= win/2, so at most two windows overlap anywhere
     n = 1 if n_samples <= win else 1 + math.ceil((n_samples - win) / step)
     return win, step, n
 
@@ -42,16 +42,15 @@ def stitch(windows, indices, n_windows, n_samples, hop, frames=696):
     """Cross-fade overlapping windows ([n, win] for the global `indices`) back into [n_samples]."""
     win, step, _ = window_plan(n_samples, hop, frames)
     total = win + (n_windows - 1) * step
-    fade = torch.hann_window(2 * step, periodic=True, dtype=torch.float64, device=windows.device)
+    ov = win - step                              # samples shared by consecutive windows
+    fade = torch.hann_window(2 * ov, periodic=True, dtype=torch.float64, device=windows.device)
     out = torch.zeros(total, dtype=torch.float64, device=windows.device)
     for w, i in zip(windows, indices):
         g = torch.ones(win, dtype=torch.float64, device=windows.device)
         if i > 0:
-            g[:step] = fade[:step]
+            g[:ov] = fade[:ov]                   # rising half; the falling half of window i-1 complements it
         if i < n_windows - 1:
-            g[win - step:] = fade[step:]
-        if win > 2 * step:      # odd remainder between the two fades keeps full weight
-            pass
+            g[win - ov:] = fade[ov:]
         out[i * step:i * step + win] += w.double() * g
     return out[:n_samples].float()
 
