@@ -116,6 +116,42 @@ int pg_bn_act(const float* y, int B, int L, int C, int rows, int ld, const float
 int pg_transpose(const float* src, int B, int R, int S, int64_t src_batch_stride, float* dst,
                  uint16_t* dst_hi, uint16_t* dst_lo, int64_t dst_batch_stride, int dst_ld, pg_stream stream);
 
+/* ---------------------------------------------------------------- training step (train.py:37-62)
+ * Replace loss.backward() (autograd through cuDNN, train.py:61), the loss of train.py:45-60 and
+ * torch.optim.Adam (train.py:26-27,62).  Gradients w.r.t. activations flow as fp32 channels-last
+ * buffers; the data gradient of a layer is the forward kernel run on the mirrored geometry
+ * (pg_conv_tc / pg_conv_simt with kind swapped and the weight packed with the other `kind`). */
+
+/* loss3[0..3] = total, MSE(cos), MSE(sin), MSE(mag); total = cos + sin + mag_weight*mag (0.2 at
+ * train.py:60).  out [rows][2C] channels-last; d_out (may be NULL) same shape; partial: double[3*n_blocks]. */
+int pg_phase_loss(const float* out, const float* logmag, const float* phase, int64_t rows, int C,
+                  float mag_weight, float* d_out, double* partial, int n_blocks, float* loss3, pg_stream stream);
+
+typedef struct pg_grad_src {
+    const float* g;           /* upstream gradient w.r.t. an activated copy of h, fp32 [B*L][ld] */
+    int ld, ch_off;
+    float slope;              /* slope of that activation for h <= 0 (0 ReLU, 0.2 LeakyReLU, 1 identity) */
+} pg_grad_src;
+/* Backward of [conv output z -> train-mode norm -> activation fan-out] (model.py:80-83).
+ * scale_shift / mean_var: what pg_bn_finalize produced in the forward pass (batch statistics), or
+ * NULL for a layer without norm.  Outputs: dgamma, dbeta [C] (may be NULL), and dZ as operand
+ * planes [B][dz_rows][C] (dz_dtype: PG_DT_F32 / PG_DT_BF16 / PG_DT_BF16_SPLIT).  Workspace:
+ * partial float2[n_chunks*C], coef float2[C]. */
+int pg_bn_bwd(const float* z, int B, int L, int C, const float* scale_shift, const float* mean_var, float eps,
+              const pg_grad_src* g0, const pg_grad_src* g1, float* partial, int n_chunks, float* coef,
+              float* dgamma, float* dbeta, void* dz_hi, void* dz_lo, int dz_rows, int dz_dtype, pg_stream stream);
+
+/* weight gradient, packed fp32 [k][C_out][C_in]; d describes the FORWARD convolution; x = its input
+ * operand, g = dZ operand planes [B][g_rows][C_out]. */
+int pg_wgrad_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* g_hi,
+                const uint16_t* g_lo, int g_rows, float* dw_packed, pg_stream stream);
+int pg_wgrad_simt(const pg_conv_desc* d, const float* x, const float* g, int g_rows, float* dw_packed, pg_stream stream);
+/* packed [k][C_out][C_in] -> torch layout (Conv1d [C_out][C_in][k] / ConvTranspose1d [C_in][C_out][k]) */
+int pg_unpack_grad(const float* packed, int kind, int C_in, int C_out, int k, float* out, pg_stream stream);
+/* torch.optim.Adam semantics (bias-corrected, eps outside the sqrt), fp32 state; step >= 1. */
+int pg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                 float eps, int step, float grad_scale, pg_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,13 +52,14 @@ def _apply(name, x, sd, per_clip, dt):
     return _bn_train(y, sd, nkey, per_clip, dt) if nkey else y
 
 
-def unet_forward(sd, x, dtype=torch.float64, per_clip_bn=False, taps=None):
+def unet_forward(sd, x, dtype=torch.float64, per_clip_bn=False, taps=None, grad=False):
     """x [B,C,T] -> [B,2C,T]; out[:, :C] is the raw phase estimate, out[:, C:] the log-mag
     estimate (train.py:45).  ``taps`` (a dict) receives the raw conv outputs and the
-    normalised tensors of every layer for per-layer parity checks."""
+    normalised tensors of every layer for per-layer parity checks.  ``grad=True`` keeps the
+    autograd graph (used by ``loss_and_grads``)."""
     dt = dtype
     lrelu = lambda t: F.leaky_relu(t, 0.2)
-    with torch.no_grad(), torch.backends.mkldnn.flags(enabled=False):
+    with torch.set_grad_enabled(grad), torch.backends.mkldnn.flags(enabled=False):
         x = x.to(dt)
         y1 = _apply("d1", x, sd, per_clip_bn, dt)                      # model.py:90, no norm
         h2 = _apply("d2", lrelu(y1), sd, per_clip_bn, dt)              # model.py:103
@@ -84,6 +85,20 @@ def phase_loss(pred, target):
         F.mse_loss(torch.sin(pp), torch.sin(target[:, 1]))
     mag = F.mse_loss(pm, target[:, 0])
     return ang + 0.2 * mag, ang, mag
+
+
+def loss_and_grads(sd, x, target, dtype=torch.float64):
+    """train.py:42-61 on the CPU: forward (batch statistics), loss, ``loss.backward()``.
+    Returns (loss, ang_loss, mag_loss, {key: grad}) for every floating-point parameter key."""
+    keys = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    leaf = {k: sd[k].detach().to(dtype).clone().requires_grad_(True) for k in keys}
+    full = dict(sd)
+    full.update(leaf)
+    with torch.backends.mkldnn.flags(enabled=False):
+        out = unet_forward(full, x, dtype, per_clip_bn=False, grad=True)
+        loss, ang, mag = phase_loss(out, target.to(dtype))
+        loss.backward()
+    return loss.item(), ang.item(), mag.item(), {k: v.grad.detach() for k, v in leaf.items()}
 
 
 def random_state_dict(C, seed=0, dtype=torch.float32):

@@ -70,3 +70,15 @@ def test_time_axis_rule():
     for T in (26, 28, 130):
         with pytest.raises(RuntimeError):
             unet_torch.unet_forward(sd, torch.randn(1, 4, T))
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p) for p in CASES])
+def test_gradients_match_reference(path):
+    """loss.backward() of the reference (train.py:61) vs autograd through the restatement."""
+    z, sd = _load(path)
+    tgt = torch.stack([torch.from_numpy(z["x"]), torch.from_numpy(z["phi"])], 1)
+    loss, ang, mag, grads = unet_torch.loss_and_grads(sd, torch.from_numpy(z["x"]), tgt)
+    assert abs(loss - float(z["loss"])) < 1e-12
+    for k in z.files:
+        if k.startswith("grad::"):
+            assert rel_l2(grads[k[6:]].numpy(), z[k]) < 1e-10, k

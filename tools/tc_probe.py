@@ -54,10 +54,66 @@ def one(layer, tpg, bo, prec, C, L_in, B):
           f"n_ok={bool((n == L_out).all())} mean_err={e_mean:.2e} var_err={e_var:.2e}")
 
 
+def wgrad(layer, prec, C, L_in, B):
+    """tensor-core weight gradient (MN-major operands) vs the exact SIMT one."""
+    import torch
+    from phasegen import ops
+    from phasegen._lib import PRECISIONS
+    kind, k, s, p, cim, com = GEOM[layer]
+    C_in, C_out = C * cim, C * com
+    torch.manual_seed(0)
+    dev = "cuda"
+    rows = (L_in + 7) // 8 * 8
+    x = torch.zeros(B, rows, C_in, device=dev)
+    x[:, :L_in] = torch.randn(B, L_in, C_in, device=dev)
+    d = ops.conv_desc(kind, B, C_in, C_out, L_in, k, s, p, rows, C_in, PRECISIONS[prec])
+    L_out = d.L_out
+    grows = (L_out + 7) // 8 * 8
+    g = torch.zeros(B, grows, C_out, device=dev)
+    g[:, :L_out] = torch.randn(B, L_out, C_out, device=dev)
+    xh = x.to(torch.bfloat16); xl = (x - xh.float()).to(torch.bfloat16)
+    gh = g.to(torch.bfloat16); gl = (g - gh.float()).to(torch.bfloat16)
+    three = prec == "bf16x3"
+    dw_tc = torch.full((k, C_out, C_in), float("nan"), device=dev)
+    dw_si = torch.empty(k, C_out, C_in, device=dev)
+    ds = ops.conv_desc(kind, B, C_in, C_out, L_in, k, s, p, rows, C_in, 0)
+    ops.wgrad_simt(ds, x, g, grows, dw_si)
+    ops.wgrad_tc(d, xh, xl if three else None, gh, gl if three else None, grows, dw_tc)
+    torch.cuda.synchronize()
+    err = ((dw_tc - dw_si).norm() / dw_si.norm()).item()
+    # independent check of the SIMT result through torch autograd on the GPU (fp64)
+    import torch.nn.functional as F
+    xc = x[:, :L_in].double().permute(0, 2, 1)
+    w = torch.zeros((C_in, C_out, k) if kind else (C_out, C_in, k), device=dev, dtype=torch.float64, requires_grad=True)
+    y = (F.conv_transpose1d if kind else F.conv1d)(xc, w, None, s, p)
+    (y * g[:, :L_out].double().permute(0, 2, 1)).sum().backward()
+    ref = w.grad.permute(2, 1, 0) if kind else w.grad.permute(2, 0, 1)
+    e_si = ((dw_si.double() - ref).norm() / ref.norm()).item()
+    print(f"RESULT wgrad {layer} {prec} C={C} L_in={L_in} L_out={L_out} B={B}: tc_vs_simt={err:.3e} "
+          f"nan={int(torch.isnan(dw_tc).sum())} simt_vs_autograd={e_si:.3e}")
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         a = sys.argv[2:]
         one(a[0], int(a[1]), int(a[2]), a[3], int(a[4]), int(a[5]), int(a[6]))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "wgrad1":
+        a = sys.argv[2:]
+        wgrad(a[0], a[1], int(a[2]), int(a[3]), int(a[4]))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "wgrad":
+        lens = {"d1": 136, "d2": 69, "d3": 66, "d4": 31, "u4": 15, "u3": 31, "u2": 66, "u1": 69}
+        cfgs = [(l, "bf16x3", 64, lens[l], 3) for l in GEOM] + [("d1", "bf16", 64, 136, 3), ("u1", "bf16x3", 128, 65, 5),
+                                                                   ("d2", "bf16x3", 128, 349, 2), ("d4", "bf16", 128, 29, 4)]
+        for c in cfgs:
+            cmd = [sys.executable, os.path.abspath(__file__), "wgrad1"] + [str(v) for v in c]
+            try:
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
+                lines = [l for l in (r.stdout + r.stderr).splitlines() if l.startswith("RESULT") or "timeout" in l or "rror" in l]
+                print("\n".join(lines[:6]) if lines else f"NO OUTPUT {c} rc={r.returncode} {(r.stderr or '')[-300:]}", flush=True)
+            except subprocess.TimeoutExpired:
+                print(f"TIMEOUT {c}", flush=True)
         return
     # reference lengths for T=136 (C=64): d1 136->69, d2 69->66, d3 66->31, d4 31->15, u4 15->31, u3 31->66, u2 66->69, u1 69->136
     lens = {"d1": 136, "d2": 69, "d3": 66, "d4": 31, "u4": 15, "u3": 31, "u2": 66, "u1": 69}

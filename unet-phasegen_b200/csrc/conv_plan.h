@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #include "../../include/phasegen.h"
+#include "common.cuh"
 
 namespace pg {
 
@@ -41,7 +42,10 @@ static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
     if (s < 1 || s > 2 || k < 1 || k > kMaxTaps) { set_error("conv plan: stride must be 1 or 2 and k <= %d (got s=%d k=%d)", kMaxTaps, s, k); return PG_ERR_UNSUPPORTED; }
     const bool tr = d->kind == PG_CONV_TRANSPOSE;
     const int L_expect = tr ? (d->L_in - 1) * s - 2 * pad + k : (d->L_in + 2 * pad - k) / s + 1;
-    if (d->L_out != L_expect || d->L_out < 1) { set_error("conv plan: L_out %d does not match geometry (expected %d)", d->L_out, L_expect); return PG_ERR_INVALID; }
+    // a transposed convolution may be asked for up to s-1 extra rows (output_padding): that is the
+    // data gradient of a strided convolution whose input length was not "natural"
+    const bool len_ok = tr ? (d->L_out >= L_expect && d->L_out < L_expect + s) : d->L_out == L_expect;
+    if (!len_ok || d->L_out < 1) { set_error("conv plan: L_out %d does not match geometry (expected %d)", d->L_out, L_expect); return PG_ERR_INVALID; }
     p->B = d->B; p->C_in = d->C_in; p->C_out = d->C_out; p->L_in = d->L_in; p->L_out = d->L_out; p->k = k;
     p->IS = tr ? 1 : s;
     p->OS = tr ? s : 1;

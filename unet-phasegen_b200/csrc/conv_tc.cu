@@ -25,127 +25,10 @@
 // two passes over TMEM so the variance is centred) and the raw fp32 output, channels-last.
 // Persistent: grid = min(#tiles, #SMs); the tile order keeps co-resident CTAs on the same
 // weight slab (L2 reuse).  Two TMEM accumulators (2 x 256 columns) overlap epilogue and MMA.
-#include <cuda.h>
-
-#include <cstdio>
-#include <cstdlib>
-
-#include "common.cuh"
+#include "tc_ptx.cuh"
 #include "conv_plan.h"
 
 namespace pg {
-
-// ------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug becomes a trapped launch (reported error) rather than a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins) {
-        if ((spins & 1023u) == 0 && clock64() - t0 > 4000000000ll) {   // ~2 s at 1.9 GHz
-            printf("phasegen conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n",
-                   (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
-            __trap();
-        }
-    }
-}
-// Long waits (epilogue warps idle for a whole K loop): back off instead of burning issue slots.
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins) {
-        __nanosleep(ns);
-        if ((spins & 255u) == 0 && clock64() - t0 > 4000000000ll) {
-            printf("phasegen conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n",
-                   (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread for the CTA.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// mbarrier arrives once every MMA issued so far by this thread has completed.
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// Shared-memory matrix descriptor, K-major, 128-byte swizzle (8-row x 128 B atoms, 1024 B apart).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, int base_offset_mode) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                // [0,14)  start address >> 4
-    d |= (uint64_t)0 << 16;                                 // [16,30) leading byte offset (unused: one atom along K)
-    d |= (uint64_t)(1024 >> 4) << 32;                       // [32,46) stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                                 // [46,48) descriptor version (sm_100)
-    if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;   // [49,52) base offset
-    d |= (uint64_t)2 << 61;                                 // [61,64) SWIZZLE_128B
-    return d;
-}
-// Instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, M = 128.
-__device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
 
 // ------------------------------------------------------------------------------------ kernel
 struct ConvTcParams {
@@ -377,10 +260,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------- host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 static EncodeTiledFn get_encode() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -393,7 +272,7 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int encode_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                        const uint32_t* box, const char* what) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return PG_ERR_CUDA; }
@@ -408,6 +287,14 @@ static int encode_bf16(CUtensorMap* map, const void* base, int rank, const uint6
 }
 
 static int g_sm_count = 0, g_max_smem = 0;
+void device_limits(int* sm_count, int* max_smem) {
+    if (!g_sm_count) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    *sm_count = g_sm_count; *max_smem = g_max_smem;
+}
 
 }  // namespace pg
 
@@ -424,11 +311,7 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     int rc = conv_plan_build(d, &prm.plan);
     if (rc != PG_OK) return rc;
     const ConvPlan& pl = prm.plan;
-    if (!g_sm_count) {
-        int dev = 0; cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    }
+    { int a_, b_; device_limits(&a_, &b_); }
     prm.y = y; prm.stats = reinterpret_cast<float4*>(stats);
     prm.n_terms = three ? 3 : 1;
     prm.base_offset_mode = d->tc_base_offset_mode;
@@ -446,8 +329,8 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
         uint64_t dims[3] = {(uint64_t)d->C_in, (uint64_t)d->C_out, (uint64_t)d->k};
         uint64_t str[2] = {(uint64_t)d->C_in * 2, (uint64_t)d->C_in * d->C_out * 2};
         uint32_t box[3] = {64, 128, 1};
-        if ((rc = encode_bf16(&mw_hi, w_hi, 3, dims, str, box, "w_hi")) != PG_OK) return rc;
-        if ((rc = encode_bf16(&mw_lo, three ? w_lo : w_hi, 3, dims, str, box, "w_lo")) != PG_OK) return rc;
+        if ((rc = encode_bf16_map(&mw_hi, w_hi, 3, dims, str, box, "w_hi")) != PG_OK) return rc;
+        if ((rc = encode_bf16_map(&mw_lo, three ? w_lo : w_hi, 3, dims, str, box, "w_lo")) != PG_OK) return rc;
     }
     {
         // activations [B][in_rows][in_ld] viewed as {channel, parity, row / IS, clip}
@@ -456,8 +339,8 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
         uint64_t str[3] = {(uint64_t)d->in_ld * 2, (uint64_t)d->in_ld * 2 * IS, (uint64_t)d->in_rows * d->in_ld * 2};
         uint32_t box[4] = {64, 1, (uint32_t)pl.strip_rows, (uint32_t)pl.nb};
         PG_REQUIRE(d->in_rows >= ((d->L_in + IS - 1) / IS) * IS, "pg_conv_tc: in_rows %d too small for L_in %d at stride %d", d->in_rows, d->L_in, IS);
-        if ((rc = encode_bf16(&mx_hi, x_hi, 4, dims, str, box, "x_hi")) != PG_OK) return rc;
-        if ((rc = encode_bf16(&mx_lo, three ? x_lo : x_hi, 4, dims, str, box, "x_lo")) != PG_OK) return rc;
+        if ((rc = encode_bf16_map(&mx_hi, x_hi, 4, dims, str, box, "x_hi")) != PG_OK) return rc;
+        if ((rc = encode_bf16_map(&mx_lo, three ? x_lo : x_hi, 4, dims, str, box, "x_lo")) != PG_OK) return rc;
     }
     static size_t configured = 0;
     if (smem_bytes > configured) {

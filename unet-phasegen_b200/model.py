@@ -15,8 +15,13 @@ What is kept from the reference interface
     the demo.py:33-42 batch-1 loop produces -- so a whole batch of clips can be inferred at once.
   * a time axis that breaks a skip concat raises RuntimeError, as torch.cat does at model.py:113.
 
+  * under autograd (parameters requiring grad, grad mode on) ``forward`` returns a tensor whose
+    ``backward()`` runs the phasegen backward kernels and fills ``p.grad`` for every parameter, so
+    ``loss.backward(); optim.step()`` (train.py:61-62) work unchanged.
+
 What differs: the modules inside a block only *hold parameters*; arithmetic happens in
-``phasegen.unet.UNetExecutor``.  There is no CPU path: a non-CUDA input raises.
+``phasegen.unet.UNetExecutor`` / ``phasegen.train.TrainExecutor``.  There is no CPU path: a
+non-CUDA input raises.
 """
 import functools
 
@@ -92,18 +97,35 @@ def _conv_spec(m, kind):
     return _unet.ConvSpec(kind, m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0], m.padding[0])
 
 
-class _NoBackward(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, out, *params):
-        return out.view_as(out)
+class _UNetFunction(torch.autograd.Function):
+    """Forward + backward of the whole U-Net on the phasegen kernels, as one autograd node, so that
+    ``loss.backward(); optim.step()`` of train.py:61-62 work unchanged on the drop-in model."""
 
     @staticmethod
-    def backward(ctx, grad):
-        raise NotImplementedError("phasegen: the backward pass of UNetModel is not available in this build")
+    def forward(ctx, x, net, *params):
+        B, _, T = x.shape
+        ex = net.train_executor(B, T, x.device)
+        ex.load_input_cf(x)
+        dn, up = net._norm_params(x.device)
+        out_cl = ex.run(dn, up)
+        if net.training:
+            net._update_running_stats(ex)
+        ctx.net, ctx.ex, ctx.norms = net, ex, (dn, up)
+        from phasegen import ops
+        return ops.transpose(out_cl)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from phasegen import ops
+        net, ex = ctx.net, ctx.ex
+        ops.transpose(grad_out.float().contiguous(), dst=ex.d_out)        # [B,2C,T] -> channels-last
+        ex.backward(*ctx.norms)
+        return (None, None) + tuple(net._param_grads(ex))
 
 
 class UNetModel(nn.Module):
     precision = "auto"     # "auto" | "bf16x3" (fp32-class, 3 bf16 tensor-core products) | "bf16" | "fp32_simt"
+    train_precision = "auto"   # precision of forward+backward under autograd (same choices)
     phase_only = False     # compute only out[:, :C] of the last layer (what demo.py:38 / train.py:78 use)
 
     def __init__(self, input_nc, output_nc, norm_layer=nn.BatchNorm2d, gpu_ids=[]):
@@ -152,6 +174,35 @@ class UNetModel(nn.Module):
         self._ensure_packed(ex)
         return ex
 
+    def train_executor(self, B, T, device, precision=None):
+        """Executor that keeps what the backward pass needs (batch statistics, raw conv outputs)."""
+        from phasegen.train import TrainExecutor
+        levels = self._levels()
+        prec = precision or (self.train_precision if self.train_precision != "auto" else self._resolve_precision(levels))
+        key = ("train", B, T, str(device), prec)
+        ex = self._exec.get(key)
+        if ex is None:
+            ex = TrainExecutor(levels, B, T, device, prec)
+            self._exec[key] = ex
+            self._packed.pop(id(ex), None)
+        self._ensure_packed(ex)
+        return ex
+
+    def _param_grads(self, ex):
+        """Gradients in the order of self.parameters(): conv weights in torch layout, norm gamma/beta."""
+        from phasegen import ops
+        by_id = {}
+        for i, b in enumerate(self._blocks()):
+            for conv, dw, desc in ((b._parts["down"], ex.dw_dn[i], ex.dn_desc[i]), (b._parts["up"], ex.dw_up[i], ex.up_desc[i])):
+                g = torch.empty_like(conv.weight)
+                ops.unpack_grad(dw, desc.kind, g)
+                by_id[id(conv.weight)] = g
+            for norm, dgb in ((b._parts["down_norm"], ex.dgb_dn[i]), (b._parts["up_norm"], ex.dgb_up[i])):
+                if norm is not None and dgb is not None and getattr(norm, "weight", None) is not None:
+                    by_id[id(norm.weight)] = dgb[0].clone()
+                    by_id[id(norm.bias)] = dgb[1].clone()
+        return [by_id.get(id(p)) if p.requires_grad else None for p in self.parameters()]
+
     def _ensure_packed(self, ex):
         blocks = self._blocks()
         ws = [b._parts["down"].weight for b in blocks] + [b._parts["up"].weight for b in blocks]
@@ -196,6 +247,11 @@ class UNetModel(nn.Module):
             raise RuntimeError(f"expected input [B, C, T], got {tuple(x.shape)}")
         x = x.float().contiguous()
         B, Cn, T = x.shape
+        params = [p for p in self.parameters()]
+        if torch.is_grad_enabled() and not per_clip and any(p.requires_grad for p in params):
+            if Cn != self.model._parts["down"].in_channels:
+                raise RuntimeError(f"expected {self.model._parts['down'].in_channels} input channels, got {Cn}")
+            return _UNetFunction.apply(x, self, *params)
         ex = self.executor(B, T, x.device, per_clip=per_clip)
         if Cn != ex.levels[0].down.C_in:
             raise RuntimeError(f"expected {ex.levels[0].down.C_in} input channels, got {Cn}")
@@ -205,10 +261,7 @@ class UNetModel(nn.Module):
         if self.training and not per_clip and ex.C_final == ex.levels[0].up.C_out:
             self._update_running_stats(ex)
         from phasegen import ops
-        out = ops.transpose(out_cl)                           # -> [B, C_final, T]
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            out = _NoBackward.apply(out, *[p for p in self.parameters() if p.requires_grad])
-        return out
+        return ops.transpose(out_cl)                          # -> [B, C_final, T]
 
     def forward_channels_last(self, x_cl, per_clip=True, phase_only=True):
         """Fused-pipeline entry: log-magnitude [B, T, C] frame-major (as the STFT kernel writes it)

@@ -25,6 +25,10 @@ class ConvDesc(C.Structure):
         "taps_per_group", "tc_base_offset_mode", "tc_max_ctas", "max_clips_per_tile")]
 
 
+class GradSrc(C.Structure):
+    _fields_ = [("g", C.c_void_p), ("ld", C.c_int), ("ch_off", C.c_int), ("slope", C.c_float)]
+
+
 class ActDst(C.Structure):
     _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("batch_stride", C.c_int64),
                 ("ld", C.c_int), ("ch_off", C.c_int), ("dtype", C.c_int), ("slope", C.c_float)]
@@ -47,6 +51,12 @@ _SIGNATURES = {
     "pg_bn_finalize": (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _P, _P, _P]),
     "pg_bn_act": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, C.POINTER(ActDst), C.POINTER(ActDst), _P]),
     "pg_transpose": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _L, _I, _P]),
+    "pg_phase_loss": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _I, _P, _P]),
+    "pg_bn_bwd": (_I, [_P, _I, _I, _I, _P, _P, _F, C.POINTER(GradSrc), C.POINTER(GradSrc), _P, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "pg_wgrad_tc": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _I, _P, _P]),
+    "pg_wgrad_simt": (_I, [C.POINTER(ConvDesc), _P, _P, _I, _P, _P]),
+    "pg_unpack_grad": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "pg_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -160,3 +160,39 @@ def act_dst(hi, lo, batch_stride, ld, ch_off, dtype, slope):
 def bn_act(y, B, L, Cn, rows, ld, scale_shift, per_clip, dst0, dst1=None):
     _lib.call("pg_bn_act", _ptr(y), B, L, Cn, rows, ld, _ptr(scale_shift), int(per_clip),
               C.byref(dst0), C.byref(dst1) if dst1 is not None else None, _stream())
+
+
+# ------------------------------------------------------------------------- training step
+def grad_src(g, ld, ch_off, slope):
+    return _lib.GradSrc(g.data_ptr(), ld, ch_off, slope)
+
+
+def phase_loss(out_cl, logmag_cl, phase_cl, d_out, partial, loss3, mag_weight=0.2):
+    """out [B,T,2C], targets [B,T,C] channels-last -> loss3 = (total, cos, sin, mag) and d_out."""
+    B, T, C2 = out_cl.shape
+    _lib.call("pg_phase_loss", _ptr(out_cl), _ptr(logmag_cl), _ptr(phase_cl), B * T, C2 // 2, mag_weight,
+              _ptr(d_out), _ptr(partial), partial.shape[0], _ptr(loss3), _stream(), n_kernels=2)
+
+
+def bn_bwd(z, B, L, Cn, scale_shift, mean_var, eps, g0, g1, partial, coef, dgamma, dbeta, dz_hi, dz_lo, dz_rows, dz_dtype):
+    n_chunks = partial.shape[0] if partial is not None else 0
+    _lib.call("pg_bn_bwd", _ptr(z), B, L, Cn, _ptr(scale_shift), _ptr(mean_var), eps, C.byref(g0),
+              C.byref(g1) if g1 is not None else None, _ptr(partial), n_chunks, _ptr(coef), _ptr(dgamma), _ptr(dbeta),
+              _ptr(dz_hi), _ptr(dz_lo), dz_rows, dz_dtype, _stream(), n_kernels=3 if scale_shift is not None else 1)
+
+
+def wgrad_tc(desc, x_hi, x_lo, g_hi, g_lo, g_rows, dw_packed):
+    _lib.call("pg_wgrad_tc", C.byref(desc), _ptr(x_hi), _ptr(x_lo), _ptr(g_hi), _ptr(g_lo), g_rows, _ptr(dw_packed), _stream())
+
+
+def wgrad_simt(desc, x, g, g_rows, dw_packed):
+    _lib.call("pg_wgrad_simt", C.byref(desc), _ptr(x), _ptr(g), g_rows, _ptr(dw_packed), _stream())
+
+
+def unpack_grad(packed, kind, out):
+    k, C_out, C_in = packed.shape
+    _lib.call("pg_unpack_grad", _ptr(packed), kind, C_in, C_out, k, _ptr(out), _stream())
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    _lib.call("pg_adam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps, step, grad_scale, _stream())

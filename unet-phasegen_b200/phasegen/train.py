@@ -1,0 +1,178 @@
+"""Training step of the U-Net on the phasegen kernels (train.py:37-62 of the reference).
+
+``TrainExecutor`` extends the forward executor with the backward pass:
+
+    loss gradient d_out ─► for every layer, top down:
+        pg_bn_bwd      dZ = backward of [norm -> activation fan-out]  (+ dgamma, dbeta)
+        pg_wgrad_*     dW (packed [k][C_out][C_in]) from the layer's saved input operand and dZ
+        pg_conv_*      data gradient = the forward kernel on the mirrored geometry
+
+A tensor that feeds two consumers (the down path and the skip concat, model.py:113) receives both
+upstream gradients inside one pg_bn_bwd call, each masked with its own activation derivative
+(LeakyReLU(0.2) for the down path, ReLU for the skip -- the in-place quirk of model.py:80).
+"""
+import torch
+
+from . import ops
+from ._lib import (PG_CONV, PG_CONV_TRANSPOSE, PG_DT_F32, PG_PREC_FP32_SIMT)
+from .unet import UNetExecutor, _Operand, _rows
+
+N_CHUNKS = 64
+
+
+class TrainExecutor(UNetExecutor):
+    def __init__(self, levels, B, T, device, precision="bf16", **kw):
+        super().__init__(levels, B, T, device, precision, per_clip=False, keep_raw=True, **kw)
+        D, dev, prec = self.D, self.device, self.prec
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.d_out = torch.empty(B, self.T_out, self.C_final, **f32)
+        self.dz_up, self.dz_dn = [None] * D, [None] * D             # dZ operands (G of wgrad / input of dgrad)
+        self.din_up, self.din_dn = [None] * D, [None] * D           # data gradients w.r.t. each conv's input (fp32)
+        self.dgrad_up, self.dgrad_dn = [None] * D, [None] * D
+        self.dw_up, self.dw_dn = [None] * D, [None] * D
+        self.dgb_up, self.dgb_dn = [None] * D, [None] * D
+        self.ws_partial, self.ws_coef = [None] * D, [None] * D
+        for i, lv in enumerate(levels):
+            for which, desc, has_norm in (("dn", self.dn_desc[i], lv.down_norm), ("up", self.up_desc[i], lv.up_norm)):
+                dz = _Operand(B, desc.L_out, desc.C_out, prec, dev)
+                dw = torch.zeros(desc.k, desc.C_out, desc.C_in, **f32)
+                dgb = (torch.zeros(desc.C_out, **f32), torch.zeros(desc.C_out, **f32)) if has_norm else None
+                need_dgrad = not (which == "dn" and i == 0)          # the network input needs no gradient
+                din = torch.empty(B, desc.L_in, desc.C_in, **f32) if need_dgrad else None
+                mirror = ops.conv_desc(PG_CONV if desc.kind == PG_CONV_TRANSPOSE else PG_CONV_TRANSPOSE, B, desc.C_out,
+                                       desc.C_in, desc.L_out, desc.k, desc.stride, desc.pad, dz.rows, dz.ld, prec,
+                                       L_out=desc.L_in, taps_per_group=self.tpg, base_offset_mode=self.bo) if need_dgrad else None
+                if which == "dn":
+                    self.dz_dn[i], self.dw_dn[i], self.dgb_dn[i], self.din_dn[i], self.dgrad_dn[i] = dz, dw, dgb, din, mirror
+                else:
+                    self.dz_up[i], self.dw_up[i], self.dgb_up[i], self.din_up[i], self.dgrad_up[i] = dz, dw, dgb, din, mirror
+        cmax = max(max(d.C_out for d in self.dn_desc), max(d.C_out for d in self.up_desc))
+        self.partial = torch.empty(N_CHUNKS, cmax, 2, **f32)
+        self.coef = torch.empty(cmax, 2, **f32)
+        self.loss_partial = torch.empty(1024, 3, device=dev, dtype=torch.float64)
+        self.loss3 = torch.zeros(4, **f32)
+
+    def pack_weights(self, down_w, up_w):
+        """Forward operands plus the data-gradient operands: the same weight tensor packed with the
+        other `kind` (a Conv1d weight [C_out][C_in][k] read as a ConvTranspose1d weight and vice versa)."""
+        super().pack_weights(down_w, up_w)
+        tc = self.prec != PG_PREC_FP32_SIMT
+        flip = lambda k: PG_CONV if k == PG_CONV_TRANSPOSE else PG_CONV_TRANSPOSE
+        self.wd_t = [ops.pack_weight(down_w[i], flip(lv.down.kind), want_tc=tc, want_simt=not tc) if i > 0 else None
+                     for i, lv in enumerate(self.levels)]
+        self.wu_t = [ops.pack_weight(up_w[i], flip(lv.up.kind), want_tc=tc, want_simt=not tc) for i, lv in enumerate(self.levels)]
+
+    # ---------------------------------------------------------------------------------------
+    def loss(self, logmag_cl, phase_cl, mag_weight=0.2):
+        """train.py:45-60 on self.out; fills self.d_out and returns the 4-vector (total, cos, sin, mag)."""
+        ops.phase_loss(self.out, logmag_cl, phase_cl, self.d_out, self.loss_partial, self.loss3, mag_weight)
+        return self.loss3
+
+    def _layer_bwd(self, desc, z, ss, mv, eps, srcs, dz, dgb, x_operand, dw, mirror, w_t, din):
+        g0 = srcs[0]
+        g1 = srcs[1] if len(srcs) > 1 else None
+        ops.bn_bwd(z, desc.B, desc.L_out, desc.C_out, ss, mv if ss is not None else None, eps, g0, g1,
+                   self.partial if ss is not None else None, self.coef, dgb[0] if dgb else None, dgb[1] if dgb else None,
+                   dz.hi, dz.lo, dz.rows, dz.dtype)
+        if self.prec == PG_PREC_FP32_SIMT:
+            ops.wgrad_simt(desc, x_operand.hi, dz.hi, dz.rows, dw)
+            if mirror is not None:
+                ops.conv_simt(mirror, dz.hi, w_t[2], din)
+        else:
+            ops.wgrad_tc(desc, x_operand.hi, x_operand.lo, dz.hi, dz.lo, dz.rows, dw)
+            if mirror is not None:
+                ops.conv_tc(mirror, dz.hi, dz.lo, w_t[0], w_t[1], din, None)
+
+    def backward(self, dn_norm, up_norm, d_out=None):
+        """Consumes the buffers of the last run(); d_out [B][T][2C] fp32 channels-last (default: the
+        one pg_phase_loss wrote).  Leaves packed weight gradients in dw_dn/dw_up and (dgamma, dbeta)
+        in dgb_dn/dgb_up."""
+        D, lv = self.D, self.levels
+        d_out = self.d_out if d_out is None else d_out
+        eps_of = lambda n: n[2] if n is not None else 1e-5
+        # up path, outermost first
+        for i in range(D):
+            desc = self.up_desc[i]
+            if i == 0:
+                srcs = [ops.grad_src(d_out, desc.C_out, 0, 1.0)]
+            else:                                   # ReLU(n_i) sits in cat[i-1] at channel offset C_down(i-1)
+                up_in = self.din_up[i - 1]
+                srcs = [ops.grad_src(up_in, self.up_desc[i - 1].C_in, lv[i - 1].down.C_out, 0.0)]
+            x_op = self.a[i] if i == D - 1 else self.cat[i]
+            self._layer_bwd(desc, self.g[i], self.up_ss[i], self.up_mv[i], eps_of(up_norm[i]), srcs, self.dz_up[i],
+                            self.dgb_up[i], x_op, self.dw_up[i], self.dgrad_up[i], self.wu_t[i], self.din_up[i])
+        # down path, innermost first
+        for i in range(D - 1, -1, -1):
+            desc = self.dn_desc[i]
+            if i == D - 1:                          # a[D-1] = ReLU(z) feeds the innermost up conv only
+                srcs = [ops.grad_src(self.din_up[i], self.up_desc[i].C_in, 0, 0.0)]
+            else:                                   # LeakyReLU(h_i) -> down conv i+1 ; ReLU(h_i) -> cat[i][:, :C]
+                srcs = [ops.grad_src(self.din_dn[i + 1], self.dn_desc[i + 1].C_in, 0, 0.2),
+                        ops.grad_src(self.din_up[i], self.up_desc[i].C_in, 0, 0.0)]
+            x_op = self.x0 if i == 0 else self.a[i - 1]
+            has = lv[i].down_norm
+            self._layer_bwd(desc, self.z[i], self.dn_ss[i] if has else None, self.dn_mv[i] if has else None,
+                            eps_of(dn_norm[i]) if has else 1e-5, srcs, self.dz_dn[i], self.dgb_dn[i], x_op, self.dw_dn[i],
+                            self.dgrad_dn[i], self.wd_t[i], self.din_dn[i])
+
+
+class TrainStep:
+    """One optimisation step of train.py:37-62 entirely on the phasegen kernels: forward (batch
+    statistics), the cos/sin/magnitude loss, backward, gradient all-reduce over NCCL when
+    world_size > 1 (the only collective of the path), fused Adam (torch.optim.Adam defaults,
+    train.py:26-27) and the re-pack of the updated weights into the tensor-core operand layout.
+    Inputs are channels-last: log-magnitude and target phase [B, T, C]."""
+
+    def __init__(self, net, B, T, device, precision="bf16", lr=1e-3, betas=(0.9, 0.999), eps=1e-8, mag_weight=0.2):
+        import torch.distributed as dist
+        self.net, self.lr, self.betas, self.eps, self.mag_weight = net, lr, betas, eps, mag_weight
+        self.ex = net.train_executor(B, T, device, precision)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.params = [p for p in net.parameters() if p.requires_grad]
+        self.m = [torch.zeros_like(p.data) for p in self.params]
+        self.v = [torch.zeros_like(p.data) for p in self.params]
+        self.grads = [torch.zeros_like(p.data) for p in self.params]
+        self.t = 0
+        blocks = net._blocks()
+        self._conv_grad = {}
+        self._norm_grad = {}
+        for i, b in enumerate(blocks):
+            self._conv_grad[id(b._parts["down"].weight)] = ("dn", i)
+            self._conv_grad[id(b._parts["up"].weight)] = ("up", i)
+            for which, nm in (("dn", b._parts["down_norm"]), ("up", b._parts["up_norm"])):
+                if nm is not None and getattr(nm, "weight", None) is not None:
+                    self._norm_grad[id(nm.weight)] = (which, i, 0)
+                    self._norm_grad[id(nm.bias)] = (which, i, 1)
+
+    def __call__(self, logmag_cl, phase_cl):
+        import torch.distributed as dist
+        net, ex = self.net, self.ex
+        net._ensure_packed(ex)
+        ex.load_input_cl(logmag_cl)
+        dn, up = net._norm_params(logmag_cl.device)
+        ex.run(dn, up)
+        if net.training:
+            net._update_running_stats(ex)
+        loss3 = ex.loss(logmag_cl, phase_cl, self.mag_weight)
+        ex.backward(dn, up)
+        self.t += 1
+        for p, g in zip(self.params, self.grads):
+            if id(p) in self._conv_grad:
+                which, i = self._conv_grad[id(p)]
+                dw = ex.dw_dn[i] if which == "dn" else ex.dw_up[i]
+                desc = ex.dn_desc[i] if which == "dn" else ex.up_desc[i]
+                ops.unpack_grad(dw, desc.kind, g)
+            else:
+                which, i, j = self._norm_grad[id(p)]
+                g.copy_((ex.dgb_dn[i] if which == "dn" else ex.dgb_up[i])[j])
+        if self.world > 1:
+            for g in self.grads:
+                dist.all_reduce(g)
+        scale = 1.0 / self.world
+        for p, g, m, v in zip(self.params, self.grads, self.m, self.v):
+            ops.adam_step(p.data, g, m, v, self.lr, self.betas[0], self.betas[1], self.eps, self.t, scale)
+        blocks = net._blocks()
+        ws = [b._parts["down"].weight for b in blocks] + [b._parts["up"].weight for b in blocks]
+        ex.pack_weights(ws[:len(blocks)], ws[len(blocks):])
+        net._packed[id(ex)] = tuple((w.data_ptr(), w._version) for w in ws)
+        return loss3
