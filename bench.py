@@ -138,6 +138,104 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def synthetic_train_pairs(B, C, T, seed, device):
+    """"MedleyDB-shaped" pairs (SURVEY.md section 8d): z = complex N(0,1) * sigma(f) with a 1/f tilt;
+    ch0 = log1p|z|, ch1 = angle z -- what data.py:39-47 yields.  Channels-last [B, T, C]."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    sigma = 4.0 / (1.0 + torch.arange(C, dtype=torch.float32) / 32.0)
+    re = torch.randn(B, T, C, generator=g) * sigma
+    im = torch.randn(B, T, C, generator=g) * sigma
+    return torch.log1p(torch.sqrt(re * re + im * im)).contiguous().to(device), torch.atan2(im, re).contiguous().to(device)
+
+
+def run_train(args):
+    """BASELINE.json config 3: train.py step (forward, cos/sin/mag loss, backward, Adam), UNetModel(1024, 2048),
+    128-frame pairs, batch 32 per GPU, bf16 tensor-core products with fp32 accumulation and fp32 master weights,
+    data-parallel over NCCL (one gradient all-reduce per step)."""
+    import torch
+    import torch.distributed as dist
+    import model as pg_model
+    from phasegen import _lib
+    from phasegen.train import TrainStep
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    C, T, B = args.train_c, 128, args.train_batch
+    torch.manual_seed(1234)
+    net = pg_model.UNetModel(C, 2 * C).to(dev)
+    step = TrainStep(net, B, T, dev, precision=args.precision if args.precision != "bf16x3" or args.train_fp32 else "bf16")
+    lm, ph = synthetic_train_pairs(B, C, T, 100 + rank, dev)
+    host = [t.cpu().pin_memory() for t in (lm, ph)]
+    W = max(args.warmup, 3)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    losses = []
+
+    def step_resident():
+        step(lm, ph)
+
+    def step_e2e():
+        a = host[0].to(dev, non_blocking=True); b = host[1].to(dev, non_blocking=True)
+        losses.append(float(step(a, b)[0].item()))
+
+    for _ in range(W):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launches
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps)
+    value = world * B / (ms / args.steps / 1e3)
+    e2e = world * B / (ms_e2e / args.steps / 1e3)
+    flops = 3 * sum(unet_flops_per_clip(C, T, False).values()) - unet_flops_per_clip(C, T, False)["d1"]   # no dgrad for d1
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = peaks.get("bf16_tflops_sustained") or 1590.0
+    achieved = flops * B / (ms / args.steps / 1e3) / 1e12
+    if rank == 0:
+        line = {"metric": "train_samples_per_second", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16-fp32acc (fp32 master weights, fp32 Adam)", "data": "synthetic",
+                "config": {"workload": f"train.py step: UNetModel({C},{2 * C}) on [B,2,{C},{T}] log-mag/phase pairs, batch {B}/GPU, "
+                                       "forward + cos/sin/mag loss + backward + Adam(lr 1e-3)", "parallelism": f"dp{world}",
+                           "timing": "CUDA events on the launch stream, max over ranks", "l2_policy": "weights + optimizer state (>10 GB) exceed L2"},
+                "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": 2 * B * T * C * 4, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"bound": "tensor", "kernel": "whole step (conv_tc + wgrad_tc dominate)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                             "frac": achieved / peak, "traffic": None, "note": "algorithmic FLOPs: fwd + dgrad + wgrad of the 8 convolutions"},
+                "loss_trace": losses[-3:]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -147,9 +245,17 @@ def main():
     ap.add_argument("--clips", type=int, default=CLIPS_PER_GPU, help="clips per GPU per step")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32_simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+                    help="infer = BASELINE config 2 (headline, default); train = config 3 (train.py step)")
+    ap.add_argument("--train-batch", type=int, default=32)
+    ap.add_argument("--train-c", type=int, default=1024)
+    ap.add_argument("--train-fp32", action="store_true", help="train with the fp32-class bf16x3 products instead of bf16")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload == "train":
+        run_train(args)
         return
 
     import torch

@@ -53,11 +53,59 @@ def test_backward_matches_reference_gradients(path):
         assert rel_l2(grads[k].cpu().numpy(), g.numpy()) < 2e-4, k
 
 
-@pytest.mark.parametrize("prec,tol", [("bf16x3", 2e-3), ("bf16", 6e-2)])
-def test_tensor_core_backward_vs_oracle(prec, tol):
+def _cos(a, b):
+    a = np.asarray(a, np.float64).ravel(); b = np.asarray(b, np.float64).ravel()
+    return float(np.dot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b)))
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("T", [40, 136])
+def test_tensor_core_backward_kernels_on_identical_forward_state(prec, tol, T):
+    """Backward with the tensor-core kernels (wgrad_tc on MN-major operands, data gradient through
+    conv_tc on the mirrored geometry) vs the exact-fp32 SIMT backward, both started from the SAME
+    forward state.  (Started from their own forward passes the two differ by ~1e-2 in small layers
+    because a pre-activation within the forward rounding error of zero flips a ReLU/LeakyReLU
+    derivative -- a property of the network, not of the kernels; see the next test.)"""
     import model
     from phasegen import synth
-    C, B, T = 64, 3, 40
+    C, B = 64, 3
+    torch.manual_seed(11)
+    net = model.UNetModel(C, 2 * C).cuda()
+    synth.randomize_norm_affine(net, seed=12)
+    x = torch.log1p(torch.randn(B, C, T).abs() * 2.0).cuda()
+    d_out = torch.randn(B, T, 2 * C, device="cuda") * 1e-3
+    dn, up = net._norm_params(x.device)
+    exs = {}
+    for p in ("fp32_simt", prec):
+        ex = net.train_executor(B, T, x.device, precision=p)
+        ex.load_input_cf(x)
+        ex.run(dn, up)
+        exs[p] = ex
+    ref, tc = exs["fp32_simt"], exs[prec]
+    for i in range(ref.D):                      # hand the exact forward state to the tensor-core executor
+        tc.z[i].copy_(ref.z[i]); tc.g[i].copy_(ref.g[i])
+        for name in ("dn_ss", "dn_mv", "up_ss", "up_mv"):
+            if getattr(ref, name)[i] is not None:
+                getattr(tc, name)[i].copy_(getattr(ref, name)[i])
+    ref.backward(dn, up, d_out=d_out); tc.backward(dn, up, d_out=d_out)
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    for i in range(ref.D):
+        assert rel(tc.dw_up[i], ref.dw_up[i]) < tol and rel(tc.dw_dn[i], ref.dw_dn[i]) < tol, i
+        assert rel(tc.din_up[i], ref.din_up[i]) < tol, i
+        if ref.din_dn[i] is not None:
+            assert rel(tc.din_dn[i], ref.din_dn[i]) < tol, i
+        assert rel(tc.dgb_up[i][0], ref.dgb_up[i][0]) < tol and rel(tc.dgb_up[i][1], ref.dgb_up[i][1]) < tol, i
+
+
+@pytest.mark.parametrize("prec,min_cos", [("bf16x3", 0.999), ("bf16", 0.98)])
+def test_tensor_core_training_gradients_vs_oracle(prec, min_cos):
+    """End to end (own forward pass, train.py loss, loss.backward()) against float64 autograd through
+    the oracle: loss to the forward tolerance, every parameter gradient by direction (cosine), since
+    isolated activation-derivative flips make an L2 bound on small tensors meaningless."""
+    import model
+    from phasegen import synth
+    C, B, T = 64, 4, 136
     torch.manual_seed(11)
     net = model.UNetModel(C, 2 * C).cuda()
     synth.randomize_norm_affine(net, seed=12)
@@ -69,13 +117,43 @@ def test_tensor_core_backward_vs_oracle(prec, tol):
     loss = _train_py_loss(pred, x.cuda(), phi.cuda(), C)
     loss.backward()
     ref_loss, _, _, ref = unet_torch.loss_and_grads(sd, x, torch.stack([x, phi], 1))
-    assert abs(loss.item() - ref_loss) < tol * abs(ref_loss)
-    worst = 0.0
+    assert abs(loss.item() - ref_loss) < (1e-3 if prec == "bf16x3" else 3e-2) * abs(ref_loss)
+    worst = 1.0
     for k, p in net.model.named_parameters():
-        e = rel_l2(p.grad.cpu().numpy(), ref[k].numpy())
-        worst = max(worst, e)
-        assert e < tol, (k, e)
-    print(f"{prec}: worst gradient rel-L2 {worst:.2e}")
+        c = _cos(p.grad.cpu().numpy(), ref[k].numpy())
+        worst = min(worst, c)
+        assert c > min_cos, (k, c)
+    print(f"{prec}: worst gradient cosine {worst:.6f}")
+
+
+def test_data_gradient_of_strided_conv_with_unnatural_length():
+    """The data gradient of Conv1d(k4, s2, p1) on a 29-row input (14 outputs) is a transposed
+    convolution asked for one row more than its natural length (output_padding = 1)."""
+    import torch.nn.functional as F
+    from phasegen import ops
+    B, C_in, C_out, L_in, k, s, p = 5, 128, 64, 14, 4, 2, 1       # mirrored: dZ [B,14,128] -> dX [B,29,64]
+    g = torch.Generator().manual_seed(9)
+    w = torch.randn(C_in, C_out, k, generator=g).cuda() / 16            # ConvTranspose1d layout [C_in][C_out][k]
+    rows = 16
+    x = torch.zeros(B, rows, C_in, device="cuda"); x[:, :L_in] = torch.randn(B, L_in, C_in, generator=g).cuda()
+    ref = F.conv_transpose1d(x[:, :L_in].double().permute(0, 2, 1), w.double(), None, s, p, output_padding=1).permute(0, 2, 1)
+    assert ref.shape[1] == 29
+    # C_out 64 is not a tensor-core tile: exact SIMT kernel
+    ds = ops.conv_desc(ops.PG_CONV_TRANSPOSE, B, C_in, C_out, L_in, k, s, p, rows, C_in, ops.PG_PREC_FP32_SIMT, L_out=29)
+    _, _, ws = ops.pack_weight(w, ops.PG_CONV_TRANSPOSE, False, True)
+    y = torch.empty(B, 29, C_out, device="cuda")
+    ops.conv_simt(ds, x, ws, y)
+    assert float((y.double() - ref).norm() / ref.norm()) < 2e-6
+    # tensor-core kernel on a tile-sized variant
+    C_out = 128
+    w = torch.randn(C_in, C_out, k, generator=g).cuda() / 16
+    ref = F.conv_transpose1d(x[:, :L_in].double().permute(0, 2, 1), w.double(), None, s, p, output_padding=1).permute(0, 2, 1)
+    d = ops.conv_desc(ops.PG_CONV_TRANSPOSE, B, C_in, C_out, L_in, k, s, p, rows, C_in, ops.PG_PREC_BF16X3, L_out=29)
+    hi, lo, _ = ops.pack_weight(w, ops.PG_CONV_TRANSPOSE)
+    xh = x.to(torch.bfloat16); xl = (x - xh.float()).to(torch.bfloat16)
+    y = torch.full((B, 29, C_out), float("nan"), device="cuda")
+    ops.conv_tc(d, xh, xl, hi, lo, y, None)
+    assert float((y.double() - ref).norm() / ref.norm()) < 3e-5
 
 
 def test_loss_kernel_and_adam_kernel():

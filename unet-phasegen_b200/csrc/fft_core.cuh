@@ -134,6 +134,22 @@ struct Pass {
             dftR<R, INV>(&v[i * R]);
         }
     }
+    // store with a per-sample gain: real sample 2m gets win[2m], 2m+1 gets win[2m+1] (synthesis window
+    // of the inverse real transform folded into the last pass)
+    PG_HD void store_windowed(float* sre, float* sim, int t, const float* win) const {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            int j = t + i * TG;
+            int base = (j / NS) * (NS * R) + (j % NS);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                int m = base + r * NS;
+                int p = pad(m);
+                sre[p] = v[i * R + r].x * win[2 * m];
+                sim[p] = v[i * R + r].y * win[2 * m + 1];
+            }
+        }
+    }
     PG_HD void store(float* sre, float* sim, int t) const {
 #pragma unroll
         for (int i = 0; i < NB; ++i) {

@@ -30,9 +30,61 @@ template <int NC, int FR_> struct StftCfg {
     static constexpr int HOP = NFFT / 4;
     static constexpr int PL = padded_len(NC);
     static constexpr int SPAN = (FR - 1) * HOP + NFFT;      // wave samples a CTA touches
-    static constexpr size_t smem_stft() { return sizeof(float) * (2 * NFFT + SPAN + 2 * PL * FR); }
-    static constexpr size_t smem_istft() { return sizeof(float) * (2 * NFFT + 2 * PL * FR); }
+    static constexpr size_t smem_stft() { return sizeof(float) * (3 * NFFT + SPAN + 2 * PL * FR); }
+    static constexpr size_t smem_istft() { return sizeof(float) * (3 * NFFT + 2 * PL * FR); }
 };
+
+// Forward transform whose first pass takes its inputs straight from the windowed wave span
+// (z[m] = x[2m] w[2m] + i x[2m+1] w[2m+1]) instead of a staged copy.
+template <int NC>
+__device__ __forceinline__ void fft_forward_from_span(float* sre, float* sim, const cpx* tw, const float* x, const float* win, int t) {
+    using P = Plan<NC>;
+    {
+        Pass<NC, P::R0, 1, false> p;
+        static_assert(P::R0 == 16, "first pass is one radix-16 butterfly per thread");
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int m = t + r * (NC / 16);
+            const float2 xv = *reinterpret_cast<const float2*>(x + 2 * m);
+            const float2 wv = *reinterpret_cast<const float2*>(win + 2 * m);
+            p.v[r] = {xv.x * wv.x, xv.y * wv.y};
+        }
+        p.twiddle_butterfly(tw, t); p.store(sre, sim, t); __syncthreads();
+    }
+    {
+        Pass<NC, P::R1, P::R0, false> p;
+        p.load(sre, sim, t); __syncthreads();
+        p.twiddle_butterfly(tw, t); p.store(sre, sim, t); __syncthreads();
+    }
+    if (P::R2 > 1) {
+        Pass<NC, (P::R2 > 1 ? P::R2 : 2), P::R0 * P::R1, false> p;
+        p.load(sre, sim, t); __syncthreads();
+        p.twiddle_butterfly(tw, t); p.store(sre, sim, t); __syncthreads();
+    }
+}
+
+// Inverse transform whose last pass applies the synthesis window while storing.
+template <int NC>
+__device__ __forceinline__ void fft_inverse_windowed(float* sre, float* sim, const cpx* tw, const float* win, int t) {
+    using P = Plan<NC>;
+    {
+        Pass<NC, P::R0, 1, true> p;
+        p.load(sre, sim, t); __syncthreads();
+        p.twiddle_butterfly(tw, t); p.store(sre, sim, t); __syncthreads();
+    }
+    {
+        Pass<NC, P::R1, P::R0, true> p;
+        p.load(sre, sim, t); __syncthreads();
+        p.twiddle_butterfly(tw, t);
+        if (P::R2 > 1) p.store(sre, sim, t); else p.store_windowed(sre, sim, t, win);
+        __syncthreads();
+    }
+    if (P::R2 > 1) {
+        Pass<NC, (P::R2 > 1 ? P::R2 : 2), P::R0 * P::R1, true> p;
+        p.load(sre, sim, t); __syncthreads();
+        p.twiddle_butterfly(tw, t); p.store_windowed(sre, sim, t, win); __syncthreads();
+    }
+}
 
 template <int NC, bool INV>
 __device__ __forceinline__ void fft_inplace(float* sre, float* sim, const cpx* tw, int t) {
@@ -64,7 +116,8 @@ stft_kernel(const float* __restrict__ wave, int N, int T, const float2* __restri
     using Cfg = StftCfg<NC, FR>;
     extern __shared__ float smem[];
     cpx* tw = reinterpret_cast<cpx*>(smem);                 // [NFFT] exp(-2 pi i m / n_fft)
-    float* span = smem + 2 * Cfg::NFFT;                     // [SPAN]
+    float* win = smem + 2 * Cfg::NFFT;                      // [NFFT] periodic Hann
+    float* span = win + Cfg::NFFT;                          // [SPAN]
     float* bufs = span + Cfg::SPAN;                         // FR x (re[PL], im[PL])
 
     const int b = blockIdx.y;
@@ -75,6 +128,7 @@ stft_kernel(const float* __restrict__ wave, int N, int T, const float2* __restri
     for (int i = tid; i < Cfg::NFFT; i += Cfg::THREADS) {
         float2 v = __ldg(tw_g + i);
         tw[i] = {v.x, v.y};
+        win[i] = 0.5f - 0.5f * v.x;                         // Hann(n) = 0.5 - 0.5 cos(2 pi n / n_fft)
     }
     // padded sample p <-> wave index p - n_fft/2, reflected at both ends (librosa center=True)
     const int p0 = t0 * Cfg::HOP - NC;
@@ -89,17 +143,7 @@ stft_kernel(const float* __restrict__ wave, int N, int T, const float2* __restri
     const int f = tid / Cfg::TG, t = tid % Cfg::TG;
     float* sre = bufs + f * 2 * Cfg::PL;
     float* sim = sre + Cfg::PL;
-    // z[m] = x[2m] w[2m] + i x[2m+1] w[2m+1];  Hann(n) = 0.5 - 0.5 cos(2 pi n / n_fft)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        int m = t + i * Cfg::TG;
-        float2 x = *reinterpret_cast<const float2*>(span + f * Cfg::HOP + 2 * m);
-        float w0 = 0.5f - 0.5f * tw[2 * m].x, w1 = 0.5f - 0.5f * tw[2 * m + 1].x;
-        sre[pad(m)] = x.x * w0;
-        sim[pad(m)] = x.y * w1;
-    }
-    __syncthreads();
-    fft_inplace<NC, false>(sre, sim, tw, t);
+    fft_forward_from_span<NC>(sre, sim, tw, span + f * Cfg::HOP, win, t);
 
     const int frame = t0 + f;
     if (frame >= T) return;
@@ -145,7 +189,8 @@ istft_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int
     constexpr int H = Cfg::FR - 3;                          // output hop-blocks per CTA
     extern __shared__ float smem[];
     cpx* tw = reinterpret_cast<cpx*>(smem);
-    float* bufs = smem + 2 * Cfg::NFFT;
+    float* win = smem + 2 * Cfg::NFFT;
+    float* bufs = win + Cfg::NFFT;
 
     const int b = blockIdx.y;
     const int j0 = blockIdx.x * H;                          // first output hop-block
@@ -155,6 +200,7 @@ istft_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int
     for (int i = tid; i < Cfg::NFFT; i += Cfg::THREADS) {
         float2 v = __ldg(tw_g + i);
         tw[i] = {v.x, v.y};
+        win[i] = 0.5f - 0.5f * v.x;
     }
 
     const int f = tid / Cfg::TG, t = tid % Cfg::TG;
@@ -208,17 +254,9 @@ istft_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int
         if (km < NC && km != k) { sre[pad(km)] = z2.x; sim[pad(km)] = z2.y; }
     }
     __syncthreads();
-    fft_inplace<NC, true>(sre, sim, tw, t);
-
-    // x[2m] = Re z[m], x[2m+1] = Im z[m]; apply the synthesis window in place.
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        int m = t + i * Cfg::TG;
-        float w0 = 0.5f - 0.5f * tw[2 * m].x, w1 = 0.5f - 0.5f * tw[2 * m + 1].x;
-        sre[pad(m)] *= w0;
-        sim[pad(m)] *= w1;
-    }
-    __syncthreads();
+    // x[2m] = Re z[m], x[2m+1] = Im z[m]; the last pass stores them already multiplied by the
+    // synthesis window.
+    fft_inverse_windowed<NC>(sre, sim, tw, win, t);
 
     // gather overlap-add: output hop-block jb (trimmed coordinates) is covered by frames
     // jb-1 .. jb+2; within frame jb-1+q the sample sits at offset (3-q)*hop + i.
@@ -237,7 +275,7 @@ istft_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int
             int o = (3 - q) * Cfg::HOP + i;
             const float* fb = bufs + (jl + q) * 2 * Cfg::PL + ((o & 1) ? Cfg::PL : 0);
             acc += fb[pad(o >> 1)];
-            float wn = 0.5f - 0.5f * tw[o].x;
+            const float wn = win[o];
             wss += wn * wn;
         }
         float y = wss > 1.17549435e-38f ? acc / wss : acc;
