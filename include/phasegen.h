@@ -77,6 +77,9 @@ typedef struct pg_conv_desc {
     int tc_base_offset_mode;  /* tensor-core path: descriptor base-offset handling of shifted strips */
     int tc_max_ctas;          /* tensor-core path: cap on the persistent grid (0 = one per SM) */
     int max_clips_per_tile;   /* tensor-core path: clips packed into one tile for short time axes (0 = auto, 1 = off) */
+    int weights_mn_major;     /* tensor-core path: weight planes are [k][C_in][C_out] (the packed layout of the MIRRORED
+                                 layer) and are fed to the MMA as an MN-major operand: the data gradient of a layer
+                                 reuses that layer's forward weight planes, no second packing */
 } pg_conv_desc;
 
 /* weights: torch layout (Conv1d [C_out][C_in][k], ConvTranspose1d [C_in][C_out][k])
@@ -86,6 +89,9 @@ int pg_pack_weight(const float* w, int kind, int C_in, int C_out, int k, uint16_
 
 /* tcgen05 implicit GEMM.  x: bf16 planes [B][in_rows][in_ld]; y fp32 [B][out_rows][out_ld];
  * stats (may be NULL): float4 {n, mean, M2, 0} [B][P][C_out], P = pg_conv_stat_parts(). */
+/* fp32 -> bf16 hi/lo planes, elementwise (weights kept in the packed layout need no re-ordering) */
+int pg_cast_split(const float* src, int64_t n, uint16_t* hi, uint16_t* lo, pg_stream stream);
+
 int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo,
                const uint16_t* w_hi, const uint16_t* w_lo, float* y, float* stats, pg_stream stream);
 int pg_conv_stat_parts(const pg_conv_desc* d);
@@ -148,9 +154,11 @@ int pg_wgrad_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_l
 int pg_wgrad_simt(const pg_conv_desc* d, const float* x, const float* g, int g_rows, float* dw_packed, pg_stream stream);
 /* packed [k][C_out][C_in] -> torch layout (Conv1d [C_out][C_in][k] / ConvTranspose1d [C_in][C_out][k]) */
 int pg_unpack_grad(const float* packed, int kind, int C_in, int C_out, int k, float* out, pg_stream stream);
-/* torch.optim.Adam semantics (bias-corrected, eps outside the sqrt), fp32 state; step >= 1. */
+/* torch.optim.Adam semantics (bias-corrected, eps outside the sqrt), fp32 state; step >= 1.
+ * w_hi / w_lo (may be NULL): also write the updated parameter as bf16 operand planes (same element
+ * order), which fuses the re-pack of packed-layout weights into the optimiser step. */
 int pg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                 float eps, int step, float grad_scale, pg_stream stream);
+                 float eps, int step, float grad_scale, uint16_t* w_hi, uint16_t* w_lo, pg_stream stream);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,22 @@ def test_phase_only_equals_full_forward():
     assert torch.equal(ph, full[:, :, :C])
 
 
+def test_weights_keep_packed_storage_on_the_gpu():
+    """The drop-in model stores conv weights as [k][C_out][C_in] memory behind the torch-shaped
+    parameter; .cuda() and load_state_dict must keep that (else packing falls back to a transposing
+    kernel every time the weights change)."""
+    import model
+    from phasegen import ops
+    net = model.UNetModel(64, 128).cuda()
+    for b in net._blocks():
+        assert ops.packed_view(b._parts["down"].weight, ops.PG_CONV) is not None
+        assert ops.packed_view(b._parts["up"].weight, ops.PG_CONV_TRANSPOSE) is not None
+    sd = {k: v.detach().cpu().contiguous() for k, v in net.model.state_dict().items()}
+    net.model.load_state_dict(sd)
+    assert ops.packed_view(net.model.model[0].weight, ops.PG_CONV) is not None
+    assert net.model.model[0].weight.shape == (128, 64, 32)
+
+
 def test_time_axis_rule_and_errors():
     import model
     net = model.UNetModel(8, 16).cuda()

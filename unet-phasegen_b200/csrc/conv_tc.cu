@@ -39,6 +39,7 @@ struct ConvTcParams {
     int b_slot_bytes;               // bytes of one plane of a B strip (R * 128)
     int n_terms;                    // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi
     int base_offset_mode;           // descriptor base-offset handling for shifted strips
+    int a_mn;                       // weight planes are [k][C_in][C_out]: A is fed MN-major (data-gradient mode)
 };
 
 constexpr int kThreads = 192;
@@ -133,8 +134,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                             mbar_wait(emptyA + s, ph ^ 1);
                             mbar_expect_tx(fullA + s, a_bytes);
                             uint8_t* dst = a_base + (size_t)s * 2 * kATileBytes;
-                            tma_load_3d(dst, &map_w_hi, fullA + s, ch * 64, tc.co_tile * 128, tp.w_idx);
-                            if (three) tma_load_3d(dst + kATileBytes, &map_w_lo, fullA + s, ch * 64, tc.co_tile * 128, tp.w_idx);
+                            if (prm.a_mn) {     // two {64 co, 64 ci-rows} boxes: MN-major atom stacks, 8 KB apart
+                                for (int h = 0; h < 2; ++h) {
+                                    tma_load_3d(dst + h * 8192, &map_w_hi, fullA + s, tc.co_tile * 128 + h * 64, ch * 64, tp.w_idx);
+                                    if (three) tma_load_3d(dst + kATileBytes + h * 8192, &map_w_lo, fullA + s, tc.co_tile * 128 + h * 64, ch * 64, tp.w_idx);
+                                }
+                            } else {
+                                tma_load_3d(dst, &map_w_hi, fullA + s, ch * 64, tc.co_tile * 128, tp.w_idx);
+                                if (three) tma_load_3d(dst + kATileBytes, &map_w_lo, fullA + s, ch * 64, tc.co_tile * 128, tp.w_idx);
+                            }
                             ++a_it;
                         }
                     }
@@ -145,7 +153,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
         // ======================================================================= MMA issuer
         if (lane == 0) {
             uint32_t a_it = 0, b_it = 0, t_it = 0;
-            const uint32_t idesc = make_idesc_bf16(pl.n_tile);
+            const uint32_t idesc = make_idesc_bf16(pl.n_tile) | (prm.a_mn ? (1u << 15) : 0u);
+            const bool a_mn = prm.a_mn != 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_it) {
                 TileCoord tc = decode_tile(pl, tile);
                 const int acc = t_it & 1; const uint32_t acc_ph = (t_it >> 1) & 1;
@@ -177,10 +186,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                                 const uint32_t acc_c = c == 0 ? accumulate : accumulate_rest;
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk) {   // 4 x (K = 16) per 64-channel chunk
-                                    const uint64_t da_hi = make_desc_sw128(a_hi + kk * 32, 0);
+                                    const uint64_t da_hi = a_mn ? make_desc_sw128_mn(a_hi + kk * 2048, 8192) : make_desc_sw128(a_hi + kk * 32, 0);
                                     const uint64_t db_hi = make_desc_sw128(b_hi + boff + kk * 32, prm.base_offset_mode);
                                     if (three) {
-                                        const uint64_t da_lo = make_desc_sw128(a_lo + kk * 32, 0);
+                                        const uint64_t da_lo = a_mn ? make_desc_sw128_mn(a_lo + kk * 2048, 8192) : make_desc_sw128(a_lo + kk * 32, 0);
                                         const uint64_t db_lo = make_desc_sw128(b_lo + boff + kk * 32, prm.base_offset_mode);
                                         umma_bf16(dcol, da_lo, db_hi, idesc, kk == 0 ? acc_c : 1u);
                                         umma_bf16(dcol, da_hi, db_lo, idesc, 1);
@@ -315,6 +324,7 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     prm.y = y; prm.stats = reinterpret_cast<float4*>(stats);
     prm.n_terms = three ? 3 : 1;
     prm.base_offset_mode = d->tc_base_offset_mode;
+    prm.a_mn = d->weights_mn_major ? 1 : 0;
     prm.b_slot_bytes = pl.nb * pl.strip_rows * 128;
     const int fixed = 4 * prm.b_slot_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
     int nA = (g_max_smem - fixed) / (2 * kATileBytes);
@@ -326,9 +336,11 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     CUtensorMap mw_hi, mw_lo, mx_hi, mx_lo;
     {
         // weights [tap][C_out][C_in] bf16
-        uint64_t dims[3] = {(uint64_t)d->C_in, (uint64_t)d->C_out, (uint64_t)d->k};
-        uint64_t str[2] = {(uint64_t)d->C_in * 2, (uint64_t)d->C_in * d->C_out * 2};
-        uint32_t box[3] = {64, 128, 1};
+        // normal: [tap][C_out][C_in] (K = C_in contiguous); MN-major mode: [tap][C_in][C_out] (M = C_out contiguous)
+        const uint64_t inner = prm.a_mn ? d->C_out : d->C_in, outer = prm.a_mn ? d->C_in : d->C_out;
+        uint64_t dims[3] = {inner, outer, (uint64_t)d->k};
+        uint64_t str[2] = {inner * 2, inner * outer * 2};
+        uint32_t box[3] = {64, prm.a_mn ? 64u : 128u, 1};
         if ((rc = encode_bf16_map(&mw_hi, w_hi, 3, dims, str, box, "w_hi")) != PG_OK) return rc;
         if ((rc = encode_bf16_map(&mw_lo, three ? w_lo : w_hi, 3, dims, str, box, "w_lo")) != PG_OK) return rc;
     }

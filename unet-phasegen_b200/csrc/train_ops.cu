@@ -207,14 +207,22 @@ __global__ void unpack_grad_kernel(const float* __restrict__ packed, int transpo
 // ------------------------------------------------------------------------------------ Adam
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
-            float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+            float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale,
+            __nv_bfloat16* __restrict__ w_hi, __nv_bfloat16* __restrict__ w_lo) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float gi = g[i] * grad_scale;
         const float mi = b1 * m[i] + (1.f - b1) * gi;
         const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
         m[i] = mi; v[i] = vi;
         // torch.optim.Adam: p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
-        p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+        const float pi = p[i] - (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+        p[i] = pi;
+        if (w_hi) {
+            __nv_bfloat16 h, l;
+            split_bf16(pi, h, l);
+            w_hi[i] = h;
+            if (w_lo) w_lo[i] = l;
+        }
     }
 }
 
@@ -285,11 +293,12 @@ extern "C" int pg_unpack_grad(const float* packed, int kind, int C_in, int C_out
 }
 
 extern "C" int pg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                            float eps, int step, float grad_scale, pg_stream stream) {
+                            float eps, int step, float grad_scale, uint16_t* w_hi, uint16_t* w_lo, pg_stream stream) {
     PG_REQUIRE(p && g && m && v && n > 0 && step >= 1, "pg_adam_step: bad arguments");
     const float bc1 = 1.f - powf(beta1, (float)step);
     const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
     int gx = (int)((n + 255) / 256); if (gx > 148 * 32) gx = 148 * 32;
-    adam_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale);
+    adam_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale,
+                                                                             reinterpret_cast<__nv_bfloat16*>(w_hi), reinterpret_cast<__nv_bfloat16*>(w_lo));
     return check_launch("adam_kernel");
 }

@@ -155,6 +155,18 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int transposed, 
     }
 }
 
+// ------------------------------------------------------------------------------ cast/split
+__global__ void __launch_bounds__(256)
+cast_split_kernel(const float* __restrict__ src, size_t n4, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(src)[i];
+        __nv_bfloat16 h[4], l[4];
+        split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+        reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+        if (lo) reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+    }
+}
+
 // ----------------------------------------------------------------------------- transpose
 __global__ void transpose_kernel(const float* __restrict__ src, int R, int S, long long src_batch_stride,
                                  float* __restrict__ dst, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
@@ -255,6 +267,15 @@ extern "C" int pg_pack_weight(const float* w, int kind, int C_in, int C_out, int
         w, kind == PG_CONV_TRANSPOSE, C_in, C_out, k, reinterpret_cast<__nv_bfloat16*>(w_hi),
         reinterpret_cast<__nv_bfloat16*>(w_lo), w_simt);
     return check_launch("pack_weight_kernel");
+}
+
+extern "C" int pg_cast_split(const float* src, int64_t n, uint16_t* hi, uint16_t* lo, pg_stream stream) {
+    PG_REQUIRE(src && hi && n > 0 && n % 4 == 0, "pg_cast_split: bad arguments (n must be a multiple of 4)");
+    const size_t n4 = (size_t)n / 4;
+    int gx = (int)((n4 + 255) / 256); if (gx > 148 * 32) gx = 148 * 32;
+    cast_split_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, n4, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                                             reinterpret_cast<__nv_bfloat16*>(lo));
+    return check_launch("cast_split_kernel");
 }
 
 extern "C" int pg_transpose(const float* src, int B, int R, int S, int64_t src_batch_stride, float* dst, uint16_t* dst_hi,

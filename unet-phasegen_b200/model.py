@@ -72,6 +72,13 @@ class UNetBlock(nn.Module):
         down_norm = None if (self.outermost or innermost) else norm_layer(inner_nc)
         up_norm = norm_layer(outer_nc)
 
+        # Keep the logical torch shapes (checkpoint format) but lay the memory out as the kernels'
+        # packed [k][C_out][C_in]: packing for the tensor cores is then an elementwise cast and the
+        # weight gradient / optimiser work on the same order (no transposing passes per step).
+        from phasegen import ops as _ops
+        down.weight = nn.Parameter(_ops.to_packed_storage(down.weight, PG_CONV))
+        up.weight = nn.Parameter(_ops.to_packed_storage(up.weight, PG_CONV_TRANSPOSE))
+
         slots = []
         if not self.outermost:
             slots.append(nn.LeakyReLU(0.2, True))
@@ -194,22 +201,32 @@ class UNetModel(nn.Module):
         by_id = {}
         for i, b in enumerate(self._blocks()):
             for conv, dw, desc in ((b._parts["down"], ex.dw_dn[i], ex.dn_desc[i]), (b._parts["up"], ex.dw_up[i], ex.up_desc[i])):
-                g = torch.empty_like(conv.weight)
-                ops.unpack_grad(dw, desc.kind, g)
-                by_id[id(conv.weight)] = g
+                # packed [k][C_out][C_in] gradient, exposed with the weight's logical shape (a view)
+                g = dw.clone()
+                by_id[id(conv.weight)] = g.permute(2, 1, 0) if desc.kind == PG_CONV_TRANSPOSE else g.permute(1, 2, 0)
             for norm, dgb in ((b._parts["down_norm"], ex.dgb_dn[i]), (b._parts["up_norm"], ex.dgb_up[i])):
                 if norm is not None and dgb is not None and getattr(norm, "weight", None) is not None:
                     by_id[id(norm.weight)] = dgb[0].clone()
                     by_id[id(norm.bias)] = dgb[1].clone()
         return [by_id.get(id(p)) if p.requires_grad else None for p in self.parameters()]
 
-    def _ensure_packed(self, ex):
+    def _weight_stamp(self):
         blocks = self._blocks()
         ws = [b._parts["down"].weight for b in blocks] + [b._parts["up"].weight for b in blocks]
-        stamp = tuple((w.data_ptr(), w._version) for w in ws)
+        return ws, tuple((w.data_ptr(), w._version) for w in ws) + (self.__dict__.get("_native_updates", 0),)
+
+    def _ensure_packed(self, ex):
+        ws, stamp = self._weight_stamp()
         if self._packed.get(id(ex)) != stamp:
-            ex.pack_weights(ws[:len(blocks)], ws[len(blocks):])
+            n = len(ws) // 2
+            ex.pack_weights(ws[:n], ws[n:])
             self._packed[id(ex)] = stamp
+
+    def _mark_packed(self, ex):
+        """Called by the native optimiser step: it changed the weights behind autograd's back and
+        refreshed `ex`'s operand planes itself; every other executor must re-pack."""
+        self.__dict__["_native_updates"] = self.__dict__.get("_native_updates", 0) + 1
+        self._packed[id(ex)] = self._weight_stamp()[1]
 
     def _norm_params(self, device):
         dn, up = [], []

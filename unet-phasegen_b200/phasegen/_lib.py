@@ -22,7 +22,7 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "kind", "B", "C_in", "C_out", "L_in", "L_out", "k", "stride", "pad",
         "in_rows", "in_ld", "out_rows", "out_ld", "precision",
-        "taps_per_group", "tc_base_offset_mode", "tc_max_ctas", "max_clips_per_tile")]
+        "taps_per_group", "tc_base_offset_mode", "tc_max_ctas", "max_clips_per_tile", "weights_mn_major")]
 
 
 class GradSrc(C.Structure):
@@ -56,7 +56,8 @@ _SIGNATURES = {
     "pg_wgrad_tc": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _I, _P, _P]),
     "pg_wgrad_simt": (_I, [C.POINTER(ConvDesc), _P, _P, _I, _P, _P]),
     "pg_unpack_grad": (_I, [_P, _I, _I, _I, _I, _P, _P]),
-    "pg_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P]),
+    "pg_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P, _P, _P]),
+    "pg_cast_split": (_I, [_P, _L, _P, _P, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -103,12 +103,12 @@ def transpose(src, dst=None, dst_hi=None, dst_lo=None, dst_batch_stride=None, ds
 
 
 def conv_desc(kind, B, C_in, C_out, L_in, k, stride, pad, in_rows, in_ld, precision, L_out=None,
-              out_rows=None, out_ld=None, taps_per_group=0, base_offset_mode=0, max_ctas=0, max_clips_per_tile=0):
+              out_rows=None, out_ld=None, taps_per_group=0, base_offset_mode=0, max_ctas=0, max_clips_per_tile=0, weights_mn_major=0):
     if L_out is None:
         L_out = (L_in - 1) * stride - 2 * pad + k if kind == PG_CONV_TRANSPOSE else (L_in + 2 * pad - k) // stride + 1
     return ConvDesc(kind, B, C_in, C_out, L_in, L_out, k, stride, pad, in_rows, in_ld,
                     L_out if out_rows is None else out_rows, C_out if out_ld is None else out_ld,
-                    precision, taps_per_group, base_offset_mode, max_ctas, max_clips_per_tile)
+                    precision, taps_per_group, base_offset_mode, max_ctas, max_clips_per_tile, weights_mn_major)
 
 
 def pack_weight(w, kind, want_tc=True, want_simt=False):
@@ -194,5 +194,27 @@ def unpack_grad(packed, kind, out):
     _lib.call("pg_unpack_grad", _ptr(packed), kind, C_in, C_out, k, _ptr(out), _stream())
 
 
-def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
-    _lib.call("pg_adam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps, step, grad_scale, _stream())
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0, w_hi=None, w_lo=None):
+    _lib.call("pg_adam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps, step, grad_scale,
+              _ptr(w_hi), _ptr(w_lo), _stream())
+
+
+def cast_split(src, hi, lo=None):
+    """fp32 (contiguous) -> bf16 hi(/lo) planes of the same element order."""
+    _lib.call("pg_cast_split", _ptr(src), src.numel(), _ptr(hi), _ptr(lo), _stream())
+
+
+def packed_view(weight, kind):
+    """The [k][C_out][C_in] view of a Conv1d / ConvTranspose1d weight if its memory already has that
+    layout (the drop-in model stores its weights that way), else None."""
+    w = weight.detach()
+    v = w.permute(2, 1, 0) if kind == PG_CONV_TRANSPOSE else w.permute(2, 0, 1)
+    return v if v.is_contiguous() else None
+
+
+def to_packed_storage(weight, kind):
+    """Re-lay a weight tensor so that its memory is [k][C_out][C_in] while its logical shape (and
+    therefore state_dict / checkpoint format) stays the torch one."""
+    w = weight.detach()
+    packed = (w.permute(2, 1, 0) if kind == PG_CONV_TRANSPOSE else w.permute(2, 0, 1)).contiguous()
+    return packed.permute(2, 1, 0) if kind == PG_CONV_TRANSPOSE else packed.permute(1, 2, 0)

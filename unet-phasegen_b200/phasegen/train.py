@@ -39,9 +39,12 @@ class TrainExecutor(UNetExecutor):
                 dgb = (torch.zeros(desc.C_out, **f32), torch.zeros(desc.C_out, **f32)) if has_norm else None
                 need_dgrad = not (which == "dn" and i == 0)          # the network input needs no gradient
                 din = torch.empty(B, desc.L_in, desc.C_in, **f32) if need_dgrad else None
+                # data gradient = the forward kernel on the mirrored geometry; on the tensor cores it reads
+                # the layer's FORWARD weight planes as an MN-major operand (no second packing)
                 mirror = ops.conv_desc(PG_CONV if desc.kind == PG_CONV_TRANSPOSE else PG_CONV_TRANSPOSE, B, desc.C_out,
                                        desc.C_in, desc.L_out, desc.k, desc.stride, desc.pad, dz.rows, dz.ld, prec,
-                                       L_out=desc.L_in, taps_per_group=self.tpg, base_offset_mode=self.bo) if need_dgrad else None
+                                       L_out=desc.L_in, taps_per_group=self.tpg, base_offset_mode=self.bo,
+                                       weights_mn_major=int(prec != PG_PREC_FP32_SIMT)) if need_dgrad else None
                 if which == "dn":
                     self.dz_dn[i], self.dw_dn[i], self.dgb_dn[i], self.din_dn[i], self.dgrad_dn[i] = dz, dw, dgb, din, mirror
                 else:
@@ -53,14 +56,18 @@ class TrainExecutor(UNetExecutor):
         self.loss3 = torch.zeros(4, **f32)
 
     def pack_weights(self, down_w, up_w):
-        """Forward operands plus the data-gradient operands: the same weight tensor packed with the
-        other `kind` (a Conv1d weight [C_out][C_in][k] read as a ConvTranspose1d weight and vice versa)."""
+        """Forward operands; the SIMT path additionally packs each weight with the other `kind` for the
+        data gradient (a Conv1d weight [C_out][C_in][k] read as a ConvTranspose1d weight and vice
+        versa).  The tensor-core data gradient needs nothing extra."""
         super().pack_weights(down_w, up_w)
-        tc = self.prec != PG_PREC_FP32_SIMT
-        flip = lambda k: PG_CONV if k == PG_CONV_TRANSPOSE else PG_CONV_TRANSPOSE
-        self.wd_t = [ops.pack_weight(down_w[i], flip(lv.down.kind), want_tc=tc, want_simt=not tc) if i > 0 else None
-                     for i, lv in enumerate(self.levels)]
-        self.wu_t = [ops.pack_weight(up_w[i], flip(lv.up.kind), want_tc=tc, want_simt=not tc) for i, lv in enumerate(self.levels)]
+        if self.prec == PG_PREC_FP32_SIMT:
+            flip = lambda k: PG_CONV if k == PG_CONV_TRANSPOSE else PG_CONV_TRANSPOSE
+            self.wd_t = [ops.pack_weight(down_w[i].contiguous(), flip(lv.down.kind), want_tc=False, want_simt=True) if i > 0 else None
+                         for i, lv in enumerate(self.levels)]
+            self.wu_t = [ops.pack_weight(up_w[i].contiguous(), flip(lv.up.kind), want_tc=False, want_simt=True)
+                         for i, lv in enumerate(self.levels)]
+        else:
+            self.wd_t, self.wu_t = self.wd, self.wu
 
     # ---------------------------------------------------------------------------------------
     def loss(self, logmag_cl, phase_cl, mag_weight=0.2):
@@ -120,29 +127,39 @@ class TrainStep:
     """One optimisation step of train.py:37-62 entirely on the phasegen kernels: forward (batch
     statistics), the cos/sin/magnitude loss, backward, gradient all-reduce over NCCL when
     world_size > 1 (the only collective of the path), fused Adam (torch.optim.Adam defaults,
-    train.py:26-27) and the re-pack of the updated weights into the tensor-core operand layout.
-    Inputs are channels-last: log-magnitude and target phase [B, T, C]."""
+    train.py:26-27) that also writes the updated weights as bf16 tensor-core operand planes.
+    Weights, gradients and optimiser state all live in the packed [k][C_out][C_in] order, so no
+    layout conversion happens inside a step.  Inputs are channels-last: log-magnitude and target
+    phase [B, T, C]."""
 
     def __init__(self, net, B, T, device, precision="bf16", lr=1e-3, betas=(0.9, 0.999), eps=1e-8, mag_weight=0.2):
         import torch.distributed as dist
         self.net, self.lr, self.betas, self.eps, self.mag_weight = net, lr, betas, eps, mag_weight
+        blocks = net._blocks()
+        for b in blocks:                          # foreign-layout weights (e.g. assigned by the user) are re-laid once
+            for conv, kind in ((b._parts["down"], PG_CONV), (b._parts["up"], PG_CONV_TRANSPOSE)):
+                if ops.packed_view(conv.weight, kind) is None:
+                    conv.weight.data = ops.to_packed_storage(conv.weight.data, kind)
         self.ex = net.train_executor(B, T, device, precision)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        self.params = [p for p in net.parameters() if p.requires_grad]
-        self.m = [torch.zeros_like(p.data) for p in self.params]
-        self.v = [torch.zeros_like(p.data) for p in self.params]
-        self.grads = [torch.zeros_like(p.data) for p in self.params]
         self.t = 0
-        blocks = net._blocks()
-        self._conv_grad = {}
-        self._norm_grad = {}
+        ex = self.ex
+        tc = ex.prec != PG_PREC_FP32_SIMT
+        # (parameter storage, gradient buffer, bf16 planes to refresh) in packed order
+        self.items = []
         for i, b in enumerate(blocks):
-            self._conv_grad[id(b._parts["down"].weight)] = ("dn", i)
-            self._conv_grad[id(b._parts["up"].weight)] = ("up", i)
-            for which, nm in (("dn", b._parts["down_norm"]), ("up", b._parts["up_norm"])):
-                if nm is not None and getattr(nm, "weight", None) is not None:
-                    self._norm_grad[id(nm.weight)] = (which, i, 0)
-                    self._norm_grad[id(nm.bias)] = (which, i, 1)
+            for conv, kind, dw, which in ((b._parts["down"], PG_CONV, ex.dw_dn[i], "dn"), (b._parts["up"], PG_CONV_TRANSPOSE, ex.dw_up[i], "up")):
+                if not conv.weight.requires_grad:
+                    continue
+                self.items.append(dict(p=ops.packed_view(conv.weight, kind), g=dw, conv=(which, i) if tc else None))
+            for nm, dgb in ((b._parts["down_norm"], ex.dgb_dn[i]), (b._parts["up_norm"], ex.dgb_up[i])):
+                if nm is None or dgb is None or getattr(nm, "weight", None) is None:
+                    continue
+                for prm, g in ((nm.weight, dgb[0]), (nm.bias, dgb[1])):
+                    if prm.requires_grad:
+                        self.items.append(dict(p=prm.data, g=g, conv=None))
+        for it in self.items:
+            it["m"] = torch.zeros_like(it["p"]); it["v"] = torch.zeros_like(it["p"])
 
     def __call__(self, logmag_cl, phase_cl):
         import torch.distributed as dist
@@ -156,23 +173,19 @@ class TrainStep:
         loss3 = ex.loss(logmag_cl, phase_cl, self.mag_weight)
         ex.backward(dn, up)
         self.t += 1
-        for p, g in zip(self.params, self.grads):
-            if id(p) in self._conv_grad:
-                which, i = self._conv_grad[id(p)]
-                dw = ex.dw_dn[i] if which == "dn" else ex.dw_up[i]
-                desc = ex.dn_desc[i] if which == "dn" else ex.up_desc[i]
-                ops.unpack_grad(dw, desc.kind, g)
-            else:
-                which, i, j = self._norm_grad[id(p)]
-                g.copy_((ex.dgb_dn[i] if which == "dn" else ex.dgb_up[i])[j])
         if self.world > 1:
-            for g in self.grads:
-                dist.all_reduce(g)
+            for it in self.items:
+                dist.all_reduce(it["g"])
         scale = 1.0 / self.world
-        for p, g, m, v in zip(self.params, self.grads, self.m, self.v):
-            ops.adam_step(p.data, g, m, v, self.lr, self.betas[0], self.betas[1], self.eps, self.t, scale)
-        blocks = net._blocks()
-        ws = [b._parts["down"].weight for b in blocks] + [b._parts["up"].weight for b in blocks]
-        ex.pack_weights(ws[:len(blocks)], ws[len(blocks):])
-        net._packed[id(ex)] = tuple((w.data_ptr(), w._version) for w in ws)
+        for it in self.items:
+            hi = lo = None
+            if it["conv"] is not None:            # refresh the tensor-core operand planes in the same pass
+                which, i = it["conv"]
+                hi, lo = (ex.wd[i] if which == "dn" else ex.wu[i])[:2]
+            ops.adam_step(it["p"], it["g"], it["m"], it["v"], self.lr, self.betas[0], self.betas[1], self.eps, self.t, scale, hi, lo)
+        if ex.prec == PG_PREC_FP32_SIMT:          # SIMT operand layouts are re-packed from the updated weights
+            blocks = net._blocks()
+            ws = [b._parts["down"].weight for b in blocks] + [b._parts["up"].weight for b in blocks]
+            ex.pack_weights(ws[:len(blocks)], ws[len(blocks):])
+        net._mark_packed(ex)
         return loss3

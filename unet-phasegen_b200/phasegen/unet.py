@@ -161,17 +161,35 @@ class UNetExecutor:
         return stats, ss, mv
 
     # ------------------------------------------------------------------------------ weights
+    def _pack_one(self, w, kind, slice_out=None):
+        """One weight -> (hi, lo, simt).  A weight whose memory is already the packed [k][C_out][C_in]
+        order (the drop-in model's) is cast elementwise; any other layout goes through the
+        transposing pack kernel."""
+        tc = self.prec != PG_PREC_FP32_SIMT
+        if not tc:
+            if slice_out is not None:
+                w = w[:, :slice_out]
+            return ops.pack_weight(w.contiguous(), kind, want_tc=False, want_simt=True)
+        pv = ops.packed_view(w, kind)
+        if pv is None:
+            if slice_out is not None:
+                w = w[:, :slice_out]
+            return ops.pack_weight(w.contiguous(), kind, want_tc=True, want_simt=False)
+        if slice_out is not None:
+            pv = pv[:, :slice_out].contiguous()
+        hi = torch.empty(pv.shape, device=pv.device, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi) if self.prec == PG_PREC_BF16X3 else None
+        ops.cast_split(pv, hi, lo)
+        return hi, lo, None
+
     def pack_weights(self, down_w, up_w):
         """down_w/up_w: per level, the torch-layout weights.  The final up conv is sliced to
         the first C_final output channels (phase-only inference)."""
-        tc = self.prec != PG_PREC_FP32_SIMT
         self.wd, self.wu = [], []
         for i, lv in enumerate(self.levels):
-            self.wd.append(ops.pack_weight(down_w[i], lv.down.kind, want_tc=tc, want_simt=not tc))
-            w = up_w[i]
-            if i == 0 and self.C_final != lv.up.C_out:
-                w = w[:, :self.C_final].contiguous()
-            self.wu.append(ops.pack_weight(w, lv.up.kind, want_tc=tc, want_simt=not tc))
+            self.wd.append(self._pack_one(down_w[i], lv.down.kind))
+            sl = self.C_final if (i == 0 and self.C_final != lv.up.C_out) else None
+            self.wu.append(self._pack_one(up_w[i], lv.up.kind, sl))
 
     # ------------------------------------------------------------------------------ forward
     def _conv(self, desc, src, w, y, stats):
