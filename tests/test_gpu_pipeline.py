@@ -97,3 +97,21 @@ def test_shape_sweep_full_path_one_clip(n_fft, T):
     assert rel_l2(logmag[0].cpu().numpy().T, lm) < 1e-4
     assert rel_l2(phase[0].cpu().numpy().T, out[:C]) < 1e-3
     assert abs(snr_db(w, audio[0].cpu().numpy()) - snr_db(w, ref)) < 0.1
+
+
+def test_host_buffer_call_equals_device_call():
+    """PhaseGenPipeline.run_host (pinned host in/out, chunked and overlapped copies) returns exactly
+    what the device-tensor call returns, ragged last chunk included."""
+    import model
+    from phasegen import synth
+    from phasegen.pipeline import PhaseGenPipeline
+    n_fft, hop, T, B = 256, 64, 24, 7
+    torch.manual_seed(8)
+    net = model.UNetModel(n_fft // 2, n_fft).cuda()
+    pipe = PhaseGenPipeline(net, n_fft, hop)
+    h_in = synth.synthetic_waves(B, (T - 1) * hop, sr=16000, seed=9).pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+    pipe.run_host(h_in, h_out, chunks=3)
+    torch.cuda.synchronize()
+    ref = torch.cat([pipe(h_in[i:i + 3].cuda()).cpu() for i in range(0, B, 3)])
+    assert torch.equal(h_out, ref)

@@ -46,3 +46,37 @@ class PhaseGenPipeline:
         if return_intermediates:
             return audio, logmag, phase
         return audio
+
+    def run_host(self, host_in, host_out, chunks=4):
+        """End-to-end call on HOST buffers (pinned float32 [B, N] in and out): the batch is cut into
+        `chunks` sub-batches whose host->device copy, GPU work and device->host copy overlap on three
+        streams, so only the first upload and the last download are exposed.  Returns when every
+        download has been ordered on the current stream (synchronise it before reading host_out)."""
+        if host_in.is_cuda or host_out.is_cuda:
+            raise RuntimeError("run_host takes host tensors; call the pipeline directly for device tensors")
+        B = host_in.shape[0]
+        Bc = -(-B // max(1, chunks))
+        cur = torch.cuda.current_stream()
+        dev = cur.device
+        if not hasattr(self, "_copy_streams"):
+            self._copy_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        s_in, s_out = self._copy_streams
+        s_in.wait_stream(cur)
+        s_out.wait_stream(cur)
+        for c0 in range(0, B, Bc):
+            sl = slice(c0, min(B, c0 + Bc))
+            with torch.cuda.stream(s_in):
+                d_in = host_in[sl].to(dev, non_blocking=True)
+                e_in = torch.cuda.Event()
+                e_in.record(s_in)
+            cur.wait_event(e_in)
+            d_in.record_stream(cur)
+            out = self(d_in)
+            e_done = torch.cuda.Event()
+            e_done.record(cur)
+            s_out.wait_event(e_done)
+            with torch.cuda.stream(s_out):
+                host_out[sl].copy_(out, non_blocking=True)
+            out.record_stream(s_out)
+        cur.wait_stream(s_out)
+        return host_out
