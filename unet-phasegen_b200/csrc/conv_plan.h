@@ -27,6 +27,7 @@ struct ConvPlan {
     int n_chunks, n_cotiles;    // C_in / 64, C_out / 128
     int strip_rows;             // rows of one activation strip (n_tile + largest shift, rounded to 8)
     int nb;                     // clips per tile: short time axes pack several clips into one 128 x (nb*n_tile) tile
+    int acc_stages;             // TMEM accumulator stages: 2 (nb*n_tile <= 256, epilogue overlaps MMA) or 1 (up to 512 columns)
     int clip_group;             // tensor-core tile order: clips per L2-resident group (set by the launcher)
     int out_rows, out_ld;
     int n_groups[2], n_taps[2];
@@ -101,14 +102,24 @@ static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
     // empty: the weight tile is then shared by nb MMAs (one per clip).
     p->nb = 1;
     if (p->n_ntiles == 1 && d->max_clips_per_tile != 1) {
-        int nb = 256 / p->n_tile;
-        if (nb > 256 / p->strip_rows) nb = 256 / p->strip_rows;
-        if (nb > 8) nb = 8;
+        // Up to 512 accumulator columns (one TMEM stage) when the strips of that many clips still leave
+        // room for the weight ring: the weight tile, the dominant L2->SM stream for short time axes, is
+        // then shared by twice as many MMAs.  Otherwise up to 256 columns, double-buffered.
+        const int planes = d->precision == PG_PREC_BF16X3 ? 2 : 1;
+        const int max_rows = (72 * 1024) / (planes * 128);          // rows of all clips' strips in one slot
+        int nb = 512 / p->n_tile;
+        if (nb * p->strip_rows > max_rows) nb = max_rows / p->strip_rows;
+        if (nb * p->n_tile <= 256 || p->n_tile > 128) {             // not worth giving up the second stage
+            nb = 256 / p->n_tile;
+            if (nb * p->strip_rows > 256) nb = 256 / p->strip_rows;
+        }
+        if (nb > 16) nb = 16;
         if (d->max_clips_per_tile > 1 && nb > d->max_clips_per_tile) nb = d->max_clips_per_tile;
         if (nb > d->B) nb = d->B;
         if (nb < 1) nb = 1;
         p->nb = nb;
     }
+    p->acc_stages = p->nb * p->n_tile <= 256 ? 2 : 1;
     p->clip_group = d->B;
     return PG_OK;
 }

@@ -157,7 +157,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
             const bool a_mn = prm.a_mn != 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_it) {
                 TileCoord tc = decode_tile(pl, tile);
-                const int acc = t_it & 1; const uint32_t acc_ph = (t_it >> 1) & 1;
+                const int acc = pl.acc_stages == 2 ? (t_it & 1) : 0;
+                const uint32_t acc_ph = pl.acc_stages == 2 ? ((t_it >> 1) & 1) : (t_it & 1);
                 mbar_wait_sleep(accEmpty + acc, acc_ph ^ 1, 200);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
@@ -216,7 +217,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
         uint32_t t_it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_it) {
             TileCoord tc = decode_tile(pl, tile);
-            const int acc = t_it & 1; const uint32_t acc_ph = (t_it >> 1) & 1;
+            const int acc = pl.acc_stages == 2 ? (t_it & 1) : 0;
+            const uint32_t acc_ph = pl.acc_stages == 2 ? ((t_it >> 1) & 1) : (t_it & 1);
             const int m0 = tc.nt * pl.n_tile;
             const int l_phase = (pl.L_out - tc.phase + pl.OS - 1) / pl.OS;   // positions of this phase
             int n_valid = l_phase - m0; if (n_valid > pl.n_tile) n_valid = pl.n_tile; if (n_valid < 0) n_valid = 0;

@@ -32,11 +32,20 @@ class TrainExecutor(UNetExecutor):
         self.dw_up, self.dw_dn = [None] * D, [None] * D
         self.dgb_up, self.dgb_dn = [None] * D, [None] * D
         self.ws_partial, self.ws_coef = [None] * D, [None] * D
+        # all norm-parameter gradients live in one flat buffer (one small all-reduce in data-parallel runs)
+        n_norm = sum(2 * d.C_out for i, lv in enumerate(levels)
+                     for d, has in ((self.dn_desc[i], lv.down_norm), (self.up_desc[i], lv.up_norm)) if has)
+        self.dgb_flat = torch.zeros(max(n_norm, 1), **f32)
+        self.grad_hook = None                                           # called with each weight gradient once it is complete
+        off = 0
         for i, lv in enumerate(levels):
             for which, desc, has_norm in (("dn", self.dn_desc[i], lv.down_norm), ("up", self.up_desc[i], lv.up_norm)):
                 dz = _Operand(B, desc.L_out, desc.C_out, prec, dev)
                 dw = torch.zeros(desc.k, desc.C_out, desc.C_in, **f32)
-                dgb = (torch.zeros(desc.C_out, **f32), torch.zeros(desc.C_out, **f32)) if has_norm else None
+                dgb = None
+                if has_norm:
+                    dgb = (self.dgb_flat[off:off + desc.C_out], self.dgb_flat[off + desc.C_out:off + 2 * desc.C_out])
+                    off += 2 * desc.C_out
                 need_dgrad = not (which == "dn" and i == 0)          # the network input needs no gradient
                 din = torch.empty(B, desc.L_in, desc.C_in, **f32) if need_dgrad else None
                 # data gradient = the forward kernel on the mirrored geometry; on the tensor cores it reads
@@ -83,11 +92,14 @@ class TrainExecutor(UNetExecutor):
                    dz.hi, dz.lo, dz.rows, dz.dtype)
         if self.prec == PG_PREC_FP32_SIMT:
             ops.wgrad_simt(desc, x_operand.hi, dz.hi, dz.rows, dw)
-            if mirror is not None:
-                ops.conv_simt(mirror, dz.hi, w_t[2], din)
         else:
             ops.wgrad_tc(desc, x_operand.hi, x_operand.lo, dz.hi, dz.lo, dz.rows, dw)
-            if mirror is not None:
+        if self.grad_hook is not None:
+            self.grad_hook(dw)                  # e.g. start this layer's all-reduce while the rest of backward runs
+        if mirror is not None:
+            if self.prec == PG_PREC_FP32_SIMT:
+                ops.conv_simt(mirror, dz.hi, w_t[2], din)
+            else:
                 ops.conv_tc(mirror, dz.hi, dz.lo, w_t[0], w_t[1], din, None)
 
     def backward(self, dn_norm, up_norm, d_out=None):
@@ -171,11 +183,19 @@ class TrainStep:
         if net.training:
             net._update_running_stats(ex)
         loss3 = ex.loss(logmag_cl, phase_cl, self.mag_weight)
+        works = []
+        if self.world > 1:
+            # one NCCL all-reduce per weight gradient, issued as soon as that layer's wgrad is queued
+            # (the outermost transposed conv, 44 % of the parameters, goes first), overlapping the
+            # remaining dgrad / wgrad kernels; the optimiser waits for all of them
+            ex.grad_hook = lambda g: works.append(dist.all_reduce(g, async_op=True))
         ex.backward(dn, up)
+        ex.grad_hook = None
         self.t += 1
         if self.world > 1:
-            for it in self.items:
-                dist.all_reduce(it["g"])
+            works.append(dist.all_reduce(ex.dgb_flat, async_op=True))
+            for w in works:
+                w.wait()
         scale = 1.0 / self.world
         for it in self.items:
             hi = lo = None
