@@ -44,7 +44,7 @@ struct ConvTcParams {
 
 constexpr int kThreads = 192;
 constexpr int kATileBytes = 128 * 128;        // one plane: 128 co x 64 ci bf16
-constexpr int kMaxASlots = 6;
+constexpr int kMaxASlots = 8;
 
 struct TileCoord { int co_tile, phase, b0, nt; };
 
@@ -75,9 +75,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nA = prm.n_a_slots;
     const int bPlane = prm.b_slot_bytes;
-    uint8_t* a_base = smem;                                   // nA x {hi 16 KB, lo 16 KB}
-    uint8_t* b_base = a_base + (size_t)nA * 2 * kATileBytes;  // 2 x {hi bPlane, lo bPlane}
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + 4 * (size_t)bPlane);
+    const int planes = prm.n_terms == 3 ? 2 : 1;              // hi (+ lo) planes per operand slot
+    uint8_t* a_base = smem;                                   // nA x {hi 16 KB (, lo 16 KB)}
+    uint8_t* b_base = a_base + (size_t)nA * planes * kATileBytes;  // 2 x {hi bPlane (, lo bPlane)}
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + 2 * (size_t)planes * bPlane);
     uint64_t* fullA = bars;                   // [kMaxASlots]
     uint64_t* emptyA = bars + kMaxASlots;     // [kMaxASlots]
     uint64_t* fullB = bars + 2 * kMaxASlots;  // [2]
@@ -123,7 +124,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                             const int s = b_it & 1; const uint32_t ph = (b_it >> 1) & 1;
                             mbar_wait(emptyB + s, ph ^ 1);
                             mbar_expect_tx(fullB + s, b_bytes);
-                            uint8_t* dst = b_base + (size_t)s * 2 * bPlane;
+                            uint8_t* dst = b_base + (size_t)s * planes * bPlane;
                             tma_load_4d(dst, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
                             if (three) tma_load_4d(dst + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
                             ++b_it;
@@ -133,7 +134,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                             const int s = a_it % nA; const uint32_t ph = (a_it / nA) & 1;
                             mbar_wait(emptyA + s, ph ^ 1);
                             mbar_expect_tx(fullA + s, a_bytes);
-                            uint8_t* dst = a_base + (size_t)s * 2 * kATileBytes;
+                            uint8_t* dst = a_base + (size_t)s * planes * kATileBytes;
                             if (prm.a_mn) {     // two {64 co, 64 ci-rows} boxes: MN-major atom stacks, 8 KB apart
                                 for (int h = 0; h < 2; ++h) {
                                     tma_load_3d(dst + h * 8192, &map_w_hi, fullA + s, tc.co_tile * 128 + h * 64, ch * 64, tp.w_idx);
@@ -171,14 +172,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                         const int bs = b_it & 1; const uint32_t bph = (b_it >> 1) & 1;
                         mbar_wait(fullB + bs, bph);
                         tc_fence_after();
-                        const uint32_t b_hi = smem_u32(b_base + (size_t)bs * 2 * bPlane);
+                        const uint32_t b_hi = smem_u32(b_base + (size_t)bs * planes * bPlane);
                         const uint32_t b_lo = b_hi + bPlane;
                         for (int j = 0; j < grp.n_taps; ++j) {
                             const ConvTap tp = pl.taps[tc.phase][grp.first_tap + j];
                             const int as = a_it % nA; const uint32_t aph = (a_it / nA) & 1;
                             mbar_wait(fullA + as, aph);
                             tc_fence_after();
-                            const uint32_t a_hi = smem_u32(a_base + (size_t)as * 2 * kATileBytes);
+                            const uint32_t a_hi = smem_u32(a_base + (size_t)as * planes * kATileBytes);
                             const uint32_t a_lo = a_hi + kATileBytes;
                             const uint32_t sh = (uint32_t)tp.shift * 128u;
                             for (int c = 0; c < pl.nb; ++c) {      // one MMA group per clip of the bundle
@@ -328,12 +329,13 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     prm.base_offset_mode = d->tc_base_offset_mode;
     prm.a_mn = d->weights_mn_major ? 1 : 0;
     prm.b_slot_bytes = pl.nb * pl.strip_rows * 128;
-    const int fixed = 4 * prm.b_slot_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
-    int nA = (g_max_smem - fixed) / (2 * kATileBytes);
+    const int planes = three ? 2 : 1;
+    const int fixed = 2 * planes * prm.b_slot_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    int nA = (g_max_smem - fixed) / (planes * kATileBytes);
     if (nA > kMaxASlots) nA = kMaxASlots;
     PG_REQUIRE(nA >= 2, "pg_conv_tc: strip of %d rows leaves no room for the weight ring", pl.strip_rows);
     prm.n_a_slots = nA;
-    const size_t smem_bytes = (size_t)fixed + (size_t)nA * 2 * kATileBytes;
+    const size_t smem_bytes = (size_t)fixed + (size_t)nA * planes * kATileBytes;
 
     CUtensorMap mw_hi, mw_lo, mx_hi, mx_lo;
     {
