@@ -80,6 +80,8 @@ typedef struct pg_conv_desc {
     int weights_mn_major;     /* tensor-core path: weight planes are [k][C_in][C_out] (the packed layout of the MIRRORED
                                  layer) and are fed to the MMA as an MN-major operand: the data gradient of a layer
                                  reuses that layer's forward weight planes, no second packing */
+    int tc_cta_pair;          /* tensor-core path: 256-channel tiles on CTA pairs (cta_group::2 MMAs, each SM reads half
+                                 of the activation strip): 0 = auto (C_out % 256 == 0), 1 = off, 2 = required */
 } pg_conv_desc;
 
 /* weights: torch layout (Conv1d [C_out][C_in][k], ConvTranspose1d [C_in][C_out][k])

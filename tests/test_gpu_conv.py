@@ -116,6 +116,46 @@ def test_tc_conv_clip_groups_and_clip_bundles(monkeypatch):
         assert bool((st[..., 0].sum(1) == d.L_out).all()), layer
 
 
+@pytest.mark.parametrize("pair", [1, 2])
+@pytest.mark.parametrize("layer,C,L_in,B,tpg", [
+    ("d1", 128, 136, 3, 16), ("d2", 128, 69, 3, 16), ("d3", 128, 66, 5, 16), ("d4", 64, 31, 9, 16),
+    ("u4", 128, 15, 9, 16), ("u3", 128, 31, 5, 16), ("u2", 128, 66, 3, 1), ("u1", 128, 69, 3, 16),
+    ("u1", 128, 349, 40, 16), ("d1", 128, 696, 21, 16), ("d2", 128, 349, 24, 16), ("u4", 128, 85, 7, 16)])
+def test_tc_conv_cta_pairs(layer, C, L_in, B, tpg, pair):
+    """cta_group::2 tiles (pair = 2: required) against single-CTA tiles (pair = 1) and the exact SIMT
+    kernel: every layer geometry, multi-tile time axes, clip bundles, persistent loops, statistics."""
+    from phasegen import ops
+    kind, k, s, p, C_in, C_out, rows, x, w = _case(layer, C, L_in, B, seed=4)
+    ds = ops.conv_desc(kind, B, C_in, C_out, L_in, k, s, p, rows, C_in, ops.PG_PREC_FP32_SIMT)
+    hi, lo, ws = ops.pack_weight(w, kind, True, True)
+    xh = x.to(torch.bfloat16); xl = (x - xh.float()).to(torch.bfloat16)
+    ys = torch.empty(B, ds.L_out, C_out, device="cuda")
+    ops.conv_simt(ds, x, ws, ys)
+    for prec, tol in ((ops.PG_PREC_BF16X3, 3e-5), (ops.PG_PREC_BF16, 1.5e-2)):
+        three = prec == ops.PG_PREC_BF16X3
+        d = ops.conv_desc(kind, B, C_in, C_out, L_in, k, s, p, rows, C_in, prec, taps_per_group=tpg, cta_pair=pair)
+        y = torch.full((B, d.L_out, C_out), float("nan"), device="cuda")
+        st = torch.zeros(B, ops.conv_stat_parts(d), C_out, 4, device="cuda")
+        ops.conv_tc(d, xh, xl if three else None, hi, lo if three else None, y, st)
+        torch.cuda.synchronize()
+        assert not torch.isnan(y).any(), (layer, prec)
+        assert float((y - ys).norm() / ys.norm()) < tol, (layer, prec)
+        assert bool((st[..., 0].sum(1) == d.L_out).all()), (layer, prec)
+        n = st[..., 0].sum(1)
+        mean = (st[..., 0] * st[..., 1]).sum(1) / n
+        assert float((mean - y.mean(1)).abs().max()) < 1e-4, (layer, prec)
+
+
+def test_tc_conv_pair_needs_256_channels():
+    from phasegen import ops
+    x = torch.zeros(1, 32, 64, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(8, 128, 64, device="cuda", dtype=torch.bfloat16)
+    y = torch.zeros(1, 29, 128, device="cuda")
+    d = ops.conv_desc(0, 1, 64, 128, 32, 8, 1, 2, 32, 64, ops.PG_PREC_BF16X3, cta_pair=2)
+    with pytest.raises(RuntimeError, match="256"):
+        ops.conv_tc(d, x, x, w, w, y, None)
+
+
 def test_conv_argument_errors():
     from phasegen import ops
     x = torch.zeros(1, 32, 48, device="cuda", dtype=torch.bfloat16)

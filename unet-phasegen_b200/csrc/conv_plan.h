@@ -28,6 +28,8 @@ struct ConvPlan {
     int strip_rows;             // rows of one activation strip (n_tile + largest shift, rounded to 8)
     int nb;                     // clips per tile: short time axes pack several clips into one 128 x (nb*n_tile) tile
     int acc_stages;             // TMEM accumulator stages: 2 (nb*n_tile <= 256, epilogue overlaps MMA) or 1 (up to 512 columns)
+    int pair;                   // tensor-core path: tiles are 256 channels wide, owned by a CTA pair (cta_group::2); strip_rows
+                                // is then the half strip (n_tile/2 + largest shift) each CTA of the pair loads
     int clip_group;             // tensor-core tile order: clips per L2-resident group (set by the launcher)
     int out_rows, out_ld;
     int n_groups[2], n_taps[2];
@@ -96,7 +98,11 @@ static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
         for (int q = 0; q < n; ++q) p->taps[phi][q] = t[q];
         p->n_groups[phi] = ng; p->n_taps[phi] = n;
     }
-    p->strip_rows = (p->n_tile + max_shift + 7) / 8 * 8;
+    // CTA pairs: 0 = auto (whenever the output channels split into 256-wide slabs), 1 = off, 2 = required
+    p->pair = (d->tc_cta_pair != 1 && d->C_out % 256 == 0 && d->precision != PG_PREC_FP32_SIMT) ? 1 : 0;
+    if (d->tc_cta_pair == 2 && !p->pair) { set_error("conv plan: CTA pairs need C_out %% 256 == 0 (got %d)", d->C_out); return PG_ERR_INVALID; }
+    const int n_cta = p->pair ? p->n_tile / 2 : p->n_tile;        // positions of a clip whose rows one CTA loads
+    p->strip_rows = (n_cta + max_shift + 7) / 8 * 8;
     if (p->strip_rows > 256) p->strip_rows = 256;
     // Several clips per tile when one clip's positions leave the 256-column accumulator mostly
     // empty: the weight tile is then shared by nb MMAs (one per clip).

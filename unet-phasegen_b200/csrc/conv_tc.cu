@@ -25,6 +25,17 @@
 // two passes over TMEM so the variance is centred) and the raw fp32 output, channels-last.
 // Persistent: grid = min(#tiles, #SMs); the tile order keeps co-resident CTAs on the same
 // weight slab (L2 reuse).  Two TMEM accumulators (2 x 256 columns) overlap epilogue and MMA.
+//
+// CTA pairs (PAIR = true, the default whenever C_out is a multiple of 256).  In the single-CTA form
+// every MMA reads its 128 x 16 weight tile AND its N x 16 activation tile from shared memory, and the
+// measured tensor-pipe time per MMA is ~32 + N/2 cycles instead of N/2 (profiles/r01_conv_tc_ncu_full_v1.csv:
+// 72 % at N = 176): the operand reads are what paces the pipe.  A cluster of two CTAs on one TPC issues
+// cta_group::2 MMAs with M = 256 instead: CTA r owns output channels [256 t + 128 r, +128) (its own
+// weight tile, its own TMEM lanes) and supplies positions [r N/2, (r+1) N/2) of the activation strip,
+// so the activation bytes each SM reads per MMA halve.  Only the even CTA issues MMAs; both CTAs run a
+// TMA producer (bytes are counted on the even CTA's "full" barriers, cta_group::2 TMA), the "empty" and
+// "accumulator full" barriers are signalled in both CTAs by multicast commits, and the epilogue warps of
+// both CTAs release the accumulator on the even CTA's barrier.
 #include "tc_ptx.cuh"
 #include "conv_plan.h"
 
@@ -41,6 +52,8 @@ struct ConvTcParams {
     int base_offset_mode;           // descriptor base-offset handling for shifted strips
     int a_mn;                       // weight planes are [k][C_in][C_out]: A is fed MN-major (data-gradient mode)
 };
+// plan.pair = 1: tiles are 256 output channels wide and owned by a CTA pair; plan.strip_rows is then the
+// HALF strip each CTA loads (n_tile/2 + largest shift rows).
 
 constexpr int kThreads = 192;
 constexpr int kATileBytes = 128 * 128;        // one plane: 128 co x 64 ci bf16
@@ -52,10 +65,11 @@ struct TileCoord { int co_tile, phase, b0, nt; };
 // (128 output channels x one output phase) are adjacent, so co-resident CTAs share the slab and
 // the group's activations are read from HBM once and re-used from L2 by every slab.
 __device__ __forceinline__ int n_bundles(const ConvPlan& p) { return (p.B + p.nb - 1) / p.nb; }
-__device__ __forceinline__ int total_tiles(const ConvPlan& p) { return p.n_cotiles * p.OS * n_bundles(p) * p.n_ntiles; }
+__device__ __forceinline__ int n_co_slabs(const ConvPlan& p) { return p.pair ? p.n_cotiles / 2 : p.n_cotiles; }
+__device__ __forceinline__ int total_tiles(const ConvPlan& p) { return n_co_slabs(p) * p.OS * n_bundles(p) * p.n_ntiles; }
 __device__ __forceinline__ TileCoord decode_tile(const ConvPlan& p, int tile) {
     TileCoord c;
-    const int nbg = n_bundles(p), G = p.clip_group, n_slabs = p.n_cotiles * p.OS;
+    const int nbg = n_bundles(p), G = p.clip_group, n_slabs = n_co_slabs(p) * p.OS;
     const int tiles_full = n_slabs * G * p.n_ntiles;
     const int g = tile / tiles_full, r = tile % tiles_full;
     int Gg = nbg - g * G; if (Gg > G) Gg = G;
@@ -66,6 +80,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvPlan& p, int tile) {
     return c;
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
@@ -97,15 +112,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
         for (int i = 0; i < nA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(fullB + i, 1); mbar_init(emptyB + i, 1);
-            mbar_init(accFull + i, 1); mbar_init(accEmpty + i, 4);
+            mbar_init(accFull + i, 1); mbar_init(accEmpty + i, PAIR ? 8 : 4);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) { if (PAIR) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;           // 0 = leader (issues the MMAs)
+    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int half_n = pl.n_tile >> 1;                            // PAIR: positions each CTA supplies per clip
 
     if (warp == 0) {
         // ===================================================================== TMA producer
@@ -113,9 +132,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
             uint32_t a_it = 0, b_it = 0;
             const uint32_t a_bytes = (three ? 2 : 1) * kATileBytes;
             const uint32_t b_bytes = (three ? 2 : 1) * (uint32_t)bPlane;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < n_tiles; tile += tile_step) {
                 TileCoord tc = decode_tile(pl, tile);
-                const int m0 = tc.nt * pl.n_tile;
+                if (PAIR) tc.co_tile = tc.co_tile * 2 + rank;
+                const int m0 = tc.nt * pl.n_tile + (PAIR ? rank * half_n : 0);
                 const int ng = pl.n_groups[tc.phase];
                 for (int ch = 0; ch < pl.n_chunks; ++ch) {
                     for (int g = 0; g < ng; ++g) {
@@ -123,26 +143,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                         {
                             const int s = b_it & 1; const uint32_t ph = (b_it >> 1) & 1;
                             mbar_wait(emptyB + s, ph ^ 1);
-                            mbar_expect_tx(fullB + s, b_bytes);
                             uint8_t* dst = b_base + (size_t)s * planes * bPlane;
-                            tma_load_4d(dst, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
-                            if (three) tma_load_4d(dst + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
+                            if (PAIR) {
+                                if (rank == 0) mbar_expect_tx(fullB + s, 2 * b_bytes);     // both CTAs' halves
+                                tma_load_4d_pair(dst, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
+                                if (three) tma_load_4d_pair(dst + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
+                            } else {
+                                mbar_expect_tx(fullB + s, b_bytes);
+                                tma_load_4d(dst, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
+                                if (three) tma_load_4d(dst + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
+                            }
                             ++b_it;
                         }
                         for (int j = 0; j < grp.n_taps; ++j) {
                             const ConvTap tp = pl.taps[tc.phase][grp.first_tap + j];
                             const int s = a_it % nA; const uint32_t ph = (a_it / nA) & 1;
                             mbar_wait(emptyA + s, ph ^ 1);
-                            mbar_expect_tx(fullA + s, a_bytes);
+                            if (!PAIR) mbar_expect_tx(fullA + s, a_bytes);
+                            else if (rank == 0) mbar_expect_tx(fullA + s, 2 * a_bytes);
                             uint8_t* dst = a_base + (size_t)s * planes * kATileBytes;
+                            auto load_w = [&](uint8_t* d, const CUtensorMap* m, int c0, int c1) {
+                                if (PAIR) tma_load_3d_pair(d, m, fullA + s, c0, c1, tp.w_idx);
+                                else tma_load_3d(d, m, fullA + s, c0, c1, tp.w_idx);
+                            };
                             if (prm.a_mn) {     // two {64 co, 64 ci-rows} boxes: MN-major atom stacks, 8 KB apart
                                 for (int h = 0; h < 2; ++h) {
-                                    tma_load_3d(dst + h * 8192, &map_w_hi, fullA + s, tc.co_tile * 128 + h * 64, ch * 64, tp.w_idx);
-                                    if (three) tma_load_3d(dst + kATileBytes + h * 8192, &map_w_lo, fullA + s, tc.co_tile * 128 + h * 64, ch * 64, tp.w_idx);
+                                    load_w(dst + h * 8192, &map_w_hi, tc.co_tile * 128 + h * 64, ch * 64);
+                                    if (three) load_w(dst + kATileBytes + h * 8192, &map_w_lo, tc.co_tile * 128 + h * 64, ch * 64);
                                 }
                             } else {
-                                tma_load_3d(dst, &map_w_hi, fullA + s, ch * 64, tc.co_tile * 128, tp.w_idx);
-                                if (three) tma_load_3d(dst + kATileBytes, &map_w_lo, fullA + s, ch * 64, tc.co_tile * 128, tp.w_idx);
+                                load_w(dst, &map_w_hi, ch * 64, tc.co_tile * 128);
+                                if (three) load_w(dst + kATileBytes, &map_w_lo, ch * 64, tc.co_tile * 128);
                             }
                             ++a_it;
                         }
@@ -152,11 +183,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
         }
     } else if (warp == 1) {
         // ======================================================================= MMA issuer
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             uint32_t a_it = 0, b_it = 0, t_it = 0;
-            const uint32_t idesc = make_idesc_bf16(pl.n_tile) | (prm.a_mn ? (1u << 15) : 0u);
+            const uint32_t idesc = make_idesc_bf16(pl.n_tile, PAIR ? 256 : 128) | (prm.a_mn ? (1u << 15) : 0u);
             const bool a_mn = prm.a_mn != 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_it) {
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc_flag) {
+                if (PAIR) umma_bf16_pair(d, da, db, idesc, acc_flag); else umma_bf16(d, da, db, idesc, acc_flag);
+            };
+            auto commit = [&](uint64_t* bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
+            for (int tile = tile0; tile < n_tiles; tile += tile_step, ++t_it) {
                 TileCoord tc = decode_tile(pl, tile);
                 const int acc = pl.acc_stages == 2 ? (t_it & 1) : 0;
                 const uint32_t acc_ph = pl.acc_stages == 2 ? ((t_it >> 1) & 1) : (t_it & 1);
@@ -193,31 +228,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                                     if (three) {
                                         const uint64_t da_lo = a_mn ? make_desc_sw128_mn(a_lo + kk * 2048, 8192) : make_desc_sw128(a_lo + kk * 32, 0);
                                         const uint64_t db_lo = make_desc_sw128(b_lo + boff + kk * 32, prm.base_offset_mode);
-                                        umma_bf16(dcol, da_lo, db_hi, idesc, kk == 0 ? acc_c : 1u);
-                                        umma_bf16(dcol, da_hi, db_lo, idesc, 1);
-                                        umma_bf16(dcol, da_hi, db_hi, idesc, 1);
+                                        mma(dcol, da_lo, db_hi, kk == 0 ? acc_c : 1u);
+                                        mma(dcol, da_hi, db_lo, 1);
+                                        mma(dcol, da_hi, db_hi, 1);
                                     } else {
-                                        umma_bf16(dcol, da_hi, db_hi, idesc, kk == 0 ? acc_c : 1u);
+                                        mma(dcol, da_hi, db_hi, kk == 0 ? acc_c : 1u);
                                     }
                                 }
                             }
                             accumulate = 1; accumulate_rest = 1;
-                            umma_commit(emptyA + as);
+                            commit(emptyA + as);
                             ++a_it;
                         }
-                        umma_commit(emptyB + bs);
+                        commit(emptyB + bs);
                         ++b_it;
                     }
                 }
-                umma_commit(accFull + acc);
+                commit(accFull + acc);
             }
         }
     } else {
         // ========================================================================= epilogue
         const int q = warp & 3;                               // TMEM lane quarter this warp may read
         uint32_t t_it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_it) {
+        for (int tile = tile0; tile < n_tiles; tile += tile_step, ++t_it) {
             TileCoord tc = decode_tile(pl, tile);
+            if (PAIR) tc.co_tile = tc.co_tile * 2 + rank;
             const int acc = pl.acc_stages == 2 ? (t_it & 1) : 0;
             const uint32_t acc_ph = pl.acc_stages == 2 ? ((t_it >> 1) & 1) : (t_it & 1);
             const int m0 = tc.nt * pl.n_tile;
@@ -263,12 +299,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(accEmpty + acc);
+            if (lane == 0) { if (PAIR) mbar_arrive_leader(accEmpty + acc); else mbar_arrive(accEmpty + acc); }
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (PAIR) cluster_sync_all(); else __syncthreads();      // the peer's shared memory and barriers stay valid until both are done
+    if (warp == 1) { tc_fence_after(); if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------------------------- host
@@ -320,6 +356,9 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     PG_REQUIRE(d->C_in % 64 == 0 && d->C_out % 128 == 0, "pg_conv_tc: needs C_in %% 64 == 0 and C_out %% 128 == 0 (got %d, %d)", d->C_in, d->C_out);
     PG_REQUIRE(d->in_ld % 8 == 0, "pg_conv_tc: input row pitch must be a multiple of 8 elements");
     ConvTcParams prm;
+    pg_conv_desc d_local = *d;
+    if (const char* e = getenv("PG_TC_PAIR")) d_local.tc_cta_pair = atoi(e);   // A/B hook: 1 = single CTAs, 2 = require pairs
+    d = &d_local;
     int rc = conv_plan_build(d, &prm.plan);
     if (rc != PG_OK) return rc;
     const ConvPlan& pl = prm.plan;
@@ -358,11 +397,15 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
         if ((rc = encode_bf16_map(&mx_hi, x_hi, 4, dims, str, box, "x_hi")) != PG_OK) return rc;
         if ((rc = encode_bf16_map(&mx_lo, three ? x_lo : x_hi, 4, dims, str, box, "x_lo")) != PG_OK) return rc;
     }
-    static size_t configured = 0;
-    if (smem_bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        if (e != cudaSuccess) { set_error("conv_tc: cannot opt in to %zu bytes of shared memory: %s", smem_bytes, cudaGetErrorString(e)); return PG_ERR_CUDA; }
-        configured = smem_bytes;
+    const bool pair = pl.pair != 0;
+    {
+        static size_t configured[2] = {0, 0};
+        if (smem_bytes > configured[pair]) {
+            cudaError_t e = pair ? cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)
+                                 : cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+            if (e != cudaSuccess) { set_error("conv_tc: cannot opt in to %zu bytes of shared memory: %s", smem_bytes, cudaGetErrorString(e)); return PG_ERR_CUDA; }
+            configured[pair] = smem_bytes;
+        }
     }
     {
         // clips per L2-resident group: keep ~64 MB of activations hot while every weight slab passes over them
@@ -374,9 +417,21 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
         if (G > nbg) G = nbg;
         prm.plan.clip_group = G;
     }
-    const int n_tiles = pl.n_cotiles * pl.OS * ((pl.B + pl.nb - 1) / pl.nb) * pl.n_ntiles;
-    int grid = n_tiles < g_sm_count ? n_tiles : g_sm_count;
-    if (d->tc_max_ctas > 0 && grid > d->tc_max_ctas) grid = d->tc_max_ctas;
-    conv_tc_kernel<<<grid, kThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(mw_hi, mw_lo, mx_hi, mx_lo, prm);
+    const int n_tiles = (pair ? pl.n_cotiles / 2 : pl.n_cotiles) * pl.OS * ((pl.B + pl.nb - 1) / pl.nb) * pl.n_ntiles;
+    int units = pair ? g_sm_count / 2 : g_sm_count;           // persistent CTAs (or CTA pairs: one per TPC)
+    if (d->tc_max_ctas > 0 && units > (pair ? (d->tc_max_ctas + 1) / 2 : d->tc_max_ctas)) units = pair ? (d->tc_max_ctas + 1) / 2 : d->tc_max_ctas;
+    if (units > n_tiles) units = n_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pair ? 2 * units : units);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t le = pair ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, mw_hi, mw_lo, mx_hi, mx_lo, prm)
+                          : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, mw_hi, mw_lo, mx_hi, mx_lo, prm);
+    if (le != cudaSuccess) { set_error("conv_tc_kernel launch failed: %s", cudaGetErrorString(le)); return PG_ERR_CUDA; }
     return check_launch("conv_tc_kernel");
 }

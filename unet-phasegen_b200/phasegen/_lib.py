@@ -22,7 +22,7 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "kind", "B", "C_in", "C_out", "L_in", "L_out", "k", "stride", "pad",
         "in_rows", "in_ld", "out_rows", "out_ld", "precision",
-        "taps_per_group", "tc_base_offset_mode", "tc_max_ctas", "max_clips_per_tile", "weights_mn_major")]
+        "taps_per_group", "tc_base_offset_mode", "tc_max_ctas", "max_clips_per_tile", "weights_mn_major", "tc_cta_pair")]
 
 
 class GradSrc(C.Structure):

@@ -103,12 +103,12 @@ def transpose(src, dst=None, dst_hi=None, dst_lo=None, dst_batch_stride=None, ds
 
 
 def conv_desc(kind, B, C_in, C_out, L_in, k, stride, pad, in_rows, in_ld, precision, L_out=None,
-              out_rows=None, out_ld=None, taps_per_group=0, base_offset_mode=0, max_ctas=0, max_clips_per_tile=0, weights_mn_major=0):
+              out_rows=None, out_ld=None, taps_per_group=0, base_offset_mode=0, max_ctas=0, max_clips_per_tile=0, weights_mn_major=0, cta_pair=0):
     if L_out is None:
         L_out = (L_in - 1) * stride - 2 * pad + k if kind == PG_CONV_TRANSPOSE else (L_in + 2 * pad - k) // stride + 1
     return ConvDesc(kind, B, C_in, C_out, L_in, L_out, k, stride, pad, in_rows, in_ld,
                     L_out if out_rows is None else out_rows, C_out if out_ld is None else out_ld,
-                    precision, taps_per_group, base_offset_mode, max_ctas, max_clips_per_tile, weights_mn_major)
+                    precision, taps_per_group, base_offset_mode, max_ctas, max_clips_per_tile, weights_mn_major, cta_pair)
 
 
 def pack_weight(w, kind, want_tc=True, want_simt=False):
