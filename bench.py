@@ -236,6 +236,16 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+DTYPE_NAMES = {"bf16x3": "bf16x3-fp32acc", "bf16": "bf16-fp32acc", "fp32_simt": "f32", "f16x3": "f16x3-fp32acc",
+               "f16x2": "f16x2-fp32acc", "f16mix": "f16x3/f16x2-fp32acc (two-product fp16 on d1,u1,u2)"}
+MMA_NOTES = {"bf16x3": "the fp32-class mode issues 3 bf16 MMAs per algorithmic MAC, so tensor-pipe work is 3x this figure",
+             "f16x3": "3 fp16 MMAs per algorithmic MAC, so tensor-pipe work is 3x this figure",
+             "f16x2": "2 fp16 MMAs per algorithmic MAC (weights rounded to fp16), tensor-pipe work is 2x this figure",
+             "f16mix": "2 fp16 MMAs per algorithmic MAC on d1/u1/u2 (80 % of the MACs), 3 on the other five layers: "
+                       "tensor-pipe work is 2.2x this figure",
+             "bf16": "1 bf16 MMA per algorithmic MAC", "fp32_simt": ""}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -243,7 +253,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="phasegen", choices=["phasegen", "reference"])
     ap.add_argument("--clips", type=int, default=CLIPS_PER_GPU, help="clips per GPU per step")
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32_simt"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32_simt", "f16x3", "f16mix", "f16x2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="sub-batches whose copies overlap GPU work in the e2e leg")
     ap.add_argument("--workload", default="infer", choices=["infer", "train"],
@@ -360,8 +370,7 @@ def main():
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": None, "launches": n_launch, "avg_launch_ms": tot_ms / max(n_launch, 1),
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
-                "note": "algorithmic FLOPs (8 convs, phase-only last layer); the fp32-class mode issues 3 bf16 MMAs per "
-                        "algorithmic MAC, so tensor-pipe work is 3x this figure",
+                "note": "algorithmic FLOPs (8 convs, phase-only last layer); " + MMA_NOTES[args.precision],
                 "conv_share_of_step": (tot_ms / args.steps) / (ms / args.steps)}
 
     cpu = None
@@ -373,7 +382,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"bf16x3": "bf16x3-fp32acc", "bf16": "bf16-fp32acc", "fp32_simt": "f32"}[args.precision],
+                "dtype": DTYPE_NAMES[args.precision],
                 "data": "synthetic",
                 "config": {"workload": f"batched inference: {B} clips/GPU x 4 s @ 44.1 kHz (N {N}), n_fft {N_FFT}, hop {HOP}, "
                                        f"T {T}, U-Net C {C} (153 M params, random init), STFT->U-Net->ISTFT+peak-normalise",

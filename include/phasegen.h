@@ -36,15 +36,15 @@ int pg_check_device(int* sm_count, int* cc_major, int* cc_minor);
  * utils.py:120-121, the re/im split of preproc_mdb.py:94-95 (PG_STFT_REIM) and the
  * abs/log1p/angle of data.py:39-47 (PG_STFT_LOGMAG).  center=True, reflect padding, periodic
  * Hann of length n_fft.  wave [B][N] fp32 -> out_a/out_b fp32 [B][T][n_fft/2] (frame-major,
- * DC bin dropped), T = 1 + N/hop.  out_b may be NULL.  op_hi/op_lo (may be NULL): out_a as
- * bf16 hi/lo planes [B][..][n_fft/2] with op_batch_stride elements between clips -- the
- * operand of the first convolution.  twiddle: float2[n_fft] = exp(-2*pi*i*m/n_fft).
+ * DC bin dropped), T = 1 + N/hop.  out_a or out_b may be NULL.  op_hi/op_lo (may be NULL): out_a as
+ * 16-bit hi/lo planes (op_fmt: PG_FMT_BF16 or PG_FMT_F16) [B][..][n_fft/2] with op_batch_stride
+ * elements between clips -- the operand of the first convolution.  twiddle: float2[n_fft] = exp(-2*pi*i*m/n_fft).
  * n_fft in {256,512,1024,2048}, hop = n_fft/4. */
 enum { PG_STFT_LOGMAG = 0, PG_STFT_REIM = 1 };
 int pg_stft_num_frames(int n_samples, int hop);
 int pg_stft(const float* wave, int B, int N, int n_fft, int hop, const float* twiddle, int mode,
             float* out_a, float* out_b, uint16_t* op_hi, uint16_t* op_lo, int64_t op_batch_stride,
-            pg_stream stream);
+            int op_fmt, pg_stream stream);
 
 /* ---------------------------------------------------------------- ISTFT back end
  * Replaces utils.generate_audio (utils.py:11-44): zero DC row (:38-39), librosa.istft (:40:
@@ -64,8 +64,15 @@ int pg_peak_normalize(float* wave, const float* peak, int B, int N, pg_stream st
  * model.py:77-113.  A layer is: convolution -> per-channel statistics records -> finalize
  * (scale, shift) -> apply + activation written as the operand(s) of the consumer(s). */
 enum { PG_CONV = 0, PG_CONV_TRANSPOSE = 1 };
-enum { PG_PREC_FP32_SIMT = 0, PG_PREC_BF16X3 = 1, PG_PREC_BF16 = 2 };
-enum { PG_DT_NONE = 0, PG_DT_F32 = 1, PG_DT_BF16_SPLIT = 2, PG_DT_BF16 = 3 };
+/* Tensor-core precisions.  Operands are 16-bit planes (hi, lo) with x = hi + lo; fp32 accumulate.
+ *   BF16X3: Whi*Xhi + Whi*Xlo + Wlo*Xhi, bf16 planes   (rel. error per product ~2^-16)
+ *   BF16  : Whi*Xhi, bf16                              (~2^-8; the separately stated loose mode)
+ *   F16X3 : same three products on fp16 planes          (~2^-22; operands must stay inside the fp16 range)
+ *   F16X2 : Whi*Xhi + Whi*Xlo, fp16: activations exact to 2^-22, weights rounded to fp16 (2^-11, the
+ *           rounding of a TF32 operand) -- the cost of ONE TF32 pass with half of its rounding error */
+enum { PG_PREC_FP32_SIMT = 0, PG_PREC_BF16X3 = 1, PG_PREC_BF16 = 2, PG_PREC_F16X3 = 3, PG_PREC_F16X2 = 4 };
+enum { PG_DT_NONE = 0, PG_DT_F32 = 1, PG_DT_BF16_SPLIT = 2, PG_DT_BF16 = 3, PG_DT_F16_SPLIT = 4, PG_DT_F16 = 5 };
+enum { PG_FMT_BF16 = 0, PG_FMT_F16 = 1 };   /* 16-bit format of operand planes written by a kernel */
 
 typedef struct pg_conv_desc {
     int kind;                 /* PG_CONV (model.py:77) or PG_CONV_TRANSPOSE (model.py:88,94,101) */
@@ -85,14 +92,15 @@ typedef struct pg_conv_desc {
 } pg_conv_desc;
 
 /* weights: torch layout (Conv1d [C_out][C_in][k], ConvTranspose1d [C_in][C_out][k])
- * -> bf16 hi/lo planes [k][C_out][C_in] (tensor-core path) and/or fp32 [k][C_in][C_out] (SIMT). */
+ * -> 16-bit hi/lo planes [k][C_out][C_in] (tensor-core path; fmt = PG_FMT_*) and/or fp32
+ * [k][C_in][C_out] (SIMT). */
 int pg_pack_weight(const float* w, int kind, int C_in, int C_out, int k, uint16_t* w_hi,
-                   uint16_t* w_lo, float* w_simt, pg_stream stream);
+                   uint16_t* w_lo, float* w_simt, int fmt, pg_stream stream);
 
 /* tcgen05 implicit GEMM.  x: bf16 planes [B][in_rows][in_ld]; y fp32 [B][out_rows][out_ld];
  * stats (may be NULL): float4 {n, mean, M2, 0} [B][P][C_out], P = pg_conv_stat_parts(). */
-/* fp32 -> bf16 hi/lo planes, elementwise (weights kept in the packed layout need no re-ordering) */
-int pg_cast_split(const float* src, int64_t n, uint16_t* hi, uint16_t* lo, pg_stream stream);
+/* fp32 -> 16-bit hi/lo planes (fmt = PG_FMT_*), elementwise (weights kept in the packed layout need no re-ordering) */
+int pg_cast_split(const float* src, int64_t n, uint16_t* hi, uint16_t* lo, int fmt, pg_stream stream);
 
 int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo,
                const uint16_t* w_hi, const uint16_t* w_lo, float* y, float* stats, pg_stream stream);
@@ -109,7 +117,7 @@ int pg_bn_finalize(const float* stats, int B, int P, int C, int per_clip, const 
                    const float* beta, float eps, float* scale_shift, float* mean_var, pg_stream stream);
 
 typedef struct pg_act_dst {
-    void* hi; void* lo;       /* PG_DT_F32: hi = float*; PG_DT_BF16_SPLIT: two bf16 planes; PG_DT_BF16: hi only */
+    void* hi; void* lo;       /* PG_DT_F32: hi = float*; PG_DT_{BF16,F16}_SPLIT: two 16-bit planes; PG_DT_{BF16,F16}: hi only */
     int64_t batch_stride;     /* elements between clips */
     int ld, ch_off;           /* row pitch and first channel written (skip-concat offset, model.py:113) */
     int dtype;                /* PG_DT_* */
@@ -120,9 +128,9 @@ typedef struct pg_act_dst {
 int pg_bn_act(const float* y, int B, int L, int C, int rows, int ld, const float* scale_shift,
               int per_clip, const pg_act_dst* dst0, const pg_act_dst* dst1, pg_stream stream);
 
-/* [B][R][S] fp32 -> [B][S][R] fp32 and/or bf16 hi/lo planes (reference [B,C,T] <-> channels-last). */
+/* [B][R][S] fp32 -> [B][S][R] fp32 and/or 16-bit hi/lo planes (fmt = PG_FMT_*) (reference [B,C,T] <-> channels-last). */
 int pg_transpose(const float* src, int B, int R, int S, int64_t src_batch_stride, float* dst,
-                 uint16_t* dst_hi, uint16_t* dst_lo, int64_t dst_batch_stride, int dst_ld, pg_stream stream);
+                 uint16_t* dst_hi, uint16_t* dst_lo, int64_t dst_batch_stride, int dst_ld, int fmt, pg_stream stream);
 
 /* ---------------------------------------------------------------- training step (train.py:37-62)
  * Replace loss.backward() (autograd through cuDNN, train.py:61), the loss of train.py:45-60 and

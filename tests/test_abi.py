@@ -31,14 +31,14 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from phasegen import _lib
-    assert ctypes.sizeof(_lib.ConvDesc) == 19 * 4
+    assert ctypes.sizeof(_lib.ConvDesc) == 20 * 4
     assert ctypes.sizeof(_lib.ActDst) == 8 + 8 + 8 + 4 * 4
 
 
 def test_error_reporting_without_gpu_call():
     from phasegen import _lib
     lib = _lib.load()
-    d = _lib.ConvDesc(0, 1, 64, 128, 32, 999, 8, 1, 2, 32, 64, 999, 128, 1, 0, 0, 0, 0, 0)
+    d = _lib.ConvDesc(0, 1, 64, 128, 32, 999, 8, 1, 2, 32, 64, 999, 128, 1, 0, 0, 0, 0, 0, 0)
     assert lib.pg_conv_stat_parts(ctypes.byref(d)) < 0          # L_out inconsistent with geometry
     assert "L_out" in _lib.last_error()
     d.L_out = 29

@@ -45,21 +45,21 @@ def test_simt_conv_matches_torch(layer, C, scale):
 
 
 @pytest.mark.parametrize("layer", list(GEOM))
-@pytest.mark.parametrize("prec,tol", [("bf16x3", 3e-5), ("bf16", 1.5e-2)])
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 3e-5), ("bf16", 1.5e-2), ("f16x3", 3e-5), ("f16x2", 5e-4)])
 def test_tc_conv_matches_torch(layer, prec, tol):
     from phasegen import ops
     from phasegen._lib import PRECISIONS
     C, B = 64, 3
     L_in = LENS[layer]
     kind, k, s, p, C_in, C_out, rows, x, w = _case(layer, C, L_in, B, seed=1)
-    three = prec == "bf16x3"
+    pdt = torch.float16 if prec.startswith("f16") else torch.bfloat16
     d = ops.conv_desc(kind, B, C_in, C_out, L_in, k, s, p, rows, C_in, PRECISIONS[prec], taps_per_group=1)
-    hi, lo, _ = ops.pack_weight(w, kind)
-    xh = x.to(torch.bfloat16); xl = (x - xh.float()).to(torch.bfloat16)
+    hi, lo, _ = ops.pack_weight(w, kind, plane_dtype=pdt)
+    xh = x.to(pdt); xl = (x - xh.float()).to(pdt)
     y = torch.full((B, d.L_out, C_out), float("nan"), device="cuda")
     P = ops.conv_stat_parts(d)
     st = torch.zeros(B, P, C_out, 4, device="cuda")
-    ops.conv_tc(d, xh, xl if three else None, hi, lo if three else None, y, st)
+    ops.conv_tc(d, xh, xl if prec != "bf16" else None, hi, lo if prec.endswith("x3") else None, y, st)
     torch.cuda.synchronize()
     ref = _ref(kind, x[:, :L_in], w, s, p)
     assert not torch.isnan(y).any()

@@ -45,7 +45,8 @@ def test_golden_reference_outputs(path):
 
 
 @pytest.mark.parametrize("T", [24, 32, 136])
-@pytest.mark.parametrize("prec,tol_phase", [("bf16x3", 1e-3), ("fp32_simt", 1e-3), ("bf16", 5e-2)])
+@pytest.mark.parametrize("prec,tol_phase", [("bf16x3", 1e-3), ("fp32_simt", 1e-3), ("bf16", 5e-2),
+                                            ("f16x3", 1e-4), ("f16mix", 1e-3)])
 def test_tensor_core_unet_vs_oracle(T, prec, tol_phase):
     import model
     from phasegen import synth
@@ -58,10 +59,36 @@ def test_tensor_core_unet_vs_oracle(T, prec, tol_phase):
     x = torch.log1p(torch.randn(B, C, T).abs() * 2.0)
     for per_clip in (False, True):
         ref = unet_torch.unet_forward(sd, x, torch.float64, per_clip_bn=per_clip).numpy()
-        out = net.forward(x.cuda(), per_clip=per_clip).detach().cpu().numpy()
+        with torch.no_grad():                                   # inference executor (autograd has its own, bf16-only)
+            out = net.forward(x.cuda(), per_clip=per_clip).detach().cpu().numpy()
         e_phase, e_all = rel_l2(out[:, :C], ref[:, :C]), rel_l2(out, ref)
         print(f"T={T} {prec} per_clip={per_clip}: phase rel-L2 {e_phase:.2e}, all {e_all:.2e}")
         assert e_phase < tol_phase and e_all < tol_phase
+
+
+def test_f16mix_stays_inside_the_fp32_path_bound_at_the_bench_width():
+    """BASELINE shape along channels (C = 512, k = 32 reductions of 16k..65k terms), shortened in time:
+    the two-product fp16 form on d1/u1/u2 must keep the predicted phase within 1e-3 relative L2 of the
+    float64 oracle with margin, and the all-three-product fp16 form must be far inside it."""
+    import model
+    from phasegen import synth
+    C, B, T = 512, 2, 136
+    torch.manual_seed(5)
+    net = model.UNetModel(C, 2 * C).cuda()
+    synth.randomize_norm_affine(net, seed=5)
+    sd = {k: v.detach().cpu() for k, v in net.model.state_dict().items()}
+    x = torch.log1p(torch.randn(B, C, T).abs() * 2.0)
+    ref = unet_torch.unet_forward(sd, x, torch.float64, per_clip_bn=True).numpy()
+    errs = {}
+    for prec in ("f16x3", "f16mix", "bf16x3", "f16x2"):
+        net.precision = prec
+        with torch.no_grad():
+            out = net.forward(x.cuda(), per_clip=True).detach().cpu().numpy()
+        errs[prec] = rel_l2(out[:, :C], ref[:, :C])
+    print("phase rel-L2 vs float64 oracle at C=512:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["f16x3"] < 2e-4 and errs["bf16x3"] < 2e-4
+    assert errs["f16mix"] < 7e-4          # bound 1e-3, with margin
+    assert errs["f16x2"] < 2e-3           # all eight layers two-product: stated, not the fp32-path claim
 
 
 def test_phase_only_equals_full_forward():

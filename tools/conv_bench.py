@@ -41,18 +41,20 @@ def main():
             C_out //= 2
         L_in = lin[name]
         rows = (L_in + 7) // 8 * 8
-        x = torch.zeros(a.B, rows, C_in, device="cuda", dtype=torch.bfloat16)
-        x[:, :L_in] = torch.randn(a.B, L_in, C_in, device="cuda").to(torch.bfloat16)
-        xl = (torch.randn_like(x.float()) * 0.003).to(torch.bfloat16)
-        xl[:, L_in:] = 0
+        pdt = torch.float16 if a.prec.startswith("f16") else torch.bfloat16
+        xf = torch.zeros(a.B, rows, C_in, device="cuda")
+        xf[:, :L_in] = torch.randn(a.B, L_in, C_in, device="cuda").clamp_min(0)     # post-ReLU-like activations
+        x = xf.to(pdt)
+        xl = (xf - x.float()).to(pdt)
         w = torch.randn((C_in, C_out, k) if kind else (C_out, C_in, k), device="cuda") / (C_in * k) ** 0.5
-        hi, lo, _ = ops.pack_weight(w, kind)
+        hi, lo, _ = ops.pack_weight(w, kind, plane_dtype=pdt)
         d = ops.conv_desc(kind, a.B, C_in, C_out, L_in, k, s, p, rows, C_in, PRECISIONS[a.prec],
                           taps_per_group=a.tpg, max_clips_per_tile=a.nb)
         y = torch.empty(a.B, d.L_out, C_out, device="cuda")
         st = torch.empty(a.B, ops.conv_stat_parts(d), C_out, 4, device="cuda")
-        three = a.prec == "bf16x3"
-        run = lambda: ops.conv_tc(d, x, xl if three else None, hi, lo if three else None, y, st)
+        terms = {"bf16x3": 3, "f16x3": 3, "f16x2": 2, "bf16": 1}[a.prec]
+        three = terms
+        run = lambda: ops.conv_tc(d, x, xl if terms >= 2 else None, hi, lo if terms == 3 else None, y, st)
         for _ in range(2):
             run()
         torch.cuda.synchronize()
@@ -66,7 +68,7 @@ def main():
         fl = 2.0 * C_in * C_out * k * L_macs * a.B
         tot_ms += ms; tot_fl += fl
         print(f"{name}: C_in={C_in:5d} C_out={C_out:5d} L_in={L_in:4d} L_out={d.L_out:4d} {ms:8.3f} ms  "
-              f"{fl / ms / 1e9:7.1f} TFLOP/s algorithmic  x{3 if three else 1} = {fl * (3 if three else 1) / ms / 1e9:7.1f} tensor", flush=True)
+              f"{fl / ms / 1e9:7.1f} TFLOP/s algorithmic  x{three} = {fl * three / ms / 1e9:7.1f} tensor", flush=True)
     print(f"total {tot_ms:.3f} ms  {tot_fl / tot_ms / 1e9:.1f} TFLOP/s algorithmic")
 
 

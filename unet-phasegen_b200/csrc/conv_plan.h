@@ -111,7 +111,7 @@ static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
         // Up to 512 accumulator columns (one TMEM stage) when the strips of that many clips still leave
         // room for the weight ring: the weight tile, the dominant L2->SM stream for short time axes, is
         // then shared by twice as many MMAs.  Otherwise up to 256 columns, double-buffered.
-        const int planes = d->precision == PG_PREC_BF16X3 ? 2 : 1;
+        const int planes = (d->precision == PG_PREC_BF16X3 || d->precision == PG_PREC_F16X3 || d->precision == PG_PREC_F16X2) ? 2 : 1;
         const int max_rows = (72 * 1024) / (planes * 128);          // rows of all clips' strips in one slot
         int nb = 512 / p->n_tile;
         if (nb * p->strip_rows > max_rows) nb = max_rows / p->strip_rows;

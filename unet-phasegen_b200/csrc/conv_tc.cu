@@ -48,7 +48,8 @@ struct ConvTcParams {
     float4* stats;                  // [B][P][C_out] {n, mean, M2, 0}, P = OS * n_ntiles; may be null
     int n_a_slots;                  // A ring depth
     int b_slot_bytes;               // bytes of one plane of a B strip (R * 128)
-    int n_terms;                    // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi
+    int n_terms;                    // 3 = hi*hi + hi*lo + lo*hi, 2 = Whi*(Xhi + Xlo), 1 = hi*hi
+    int f16;                        // operand planes are fp16 (else bf16)
     int base_offset_mode;           // descriptor base-offset handling for shifted strips
     int a_mn;                       // weight planes are [k][C_in][C_out]: A is fed MN-major (data-gradient mode)
 };
@@ -90,10 +91,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nA = prm.n_a_slots;
     const int bPlane = prm.b_slot_bytes;
-    const int planes = prm.n_terms == 3 ? 2 : 1;              // hi (+ lo) planes per operand slot
+    const int a_planes = prm.n_terms == 3 ? 2 : 1;            // weight planes per slot: hi (+ lo)
+    const int b_planes = prm.n_terms >= 2 ? 2 : 1;            // activation planes per slot: hi (+ lo)
     uint8_t* a_base = smem;                                   // nA x {hi 16 KB (, lo 16 KB)}
-    uint8_t* b_base = a_base + (size_t)nA * planes * kATileBytes;  // 2 x {hi bPlane (, lo bPlane)}
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + 2 * (size_t)planes * bPlane);
+    uint8_t* b_base = a_base + (size_t)nA * a_planes * kATileBytes;  // 2 x {hi bPlane (, lo bPlane)}
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + 2 * (size_t)b_planes * bPlane);
     uint64_t* fullA = bars;                   // [kMaxASlots]
     uint64_t* emptyA = bars + kMaxASlots;     // [kMaxASlots]
     uint64_t* fullB = bars + 2 * kMaxASlots;  // [2]
@@ -102,13 +104,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
     uint64_t* accEmpty = accFull + 2;         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accEmpty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: provably warp-uniform, so the role branches below are uniform branches and
+    // the single-thread instructions' operands can live in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int n_tiles = total_tiles(pl);
-    const bool three = prm.n_terms == 3;
+    const bool w_lo = prm.n_terms == 3, x_lo = prm.n_terms >= 2;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_x_hi);
-        if (three) { tma_prefetch_desc(&map_w_lo); tma_prefetch_desc(&map_x_lo); }
+        if (w_lo) tma_prefetch_desc(&map_w_lo);
+        if (x_lo) tma_prefetch_desc(&map_x_lo);
         for (int i = 0; i < nA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(fullB + i, 1); mbar_init(emptyB + i, 1);
@@ -120,7 +125,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
     tc_fence_before();
     if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int rank = PAIR ? (int)cluster_ctarank() : 0;           // 0 = leader (issues the MMAs)
     const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -130,8 +135,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
         // ===================================================================== TMA producer
         if (lane == 0) {
             uint32_t a_it = 0, b_it = 0;
-            const uint32_t a_bytes = (three ? 2 : 1) * kATileBytes;
-            const uint32_t b_bytes = (three ? 2 : 1) * (uint32_t)bPlane;
+            const uint32_t a_bytes = a_planes * kATileBytes;
+            const uint32_t b_bytes = b_planes * (uint32_t)bPlane;
             for (int tile = tile0; tile < n_tiles; tile += tile_step) {
                 TileCoord tc = decode_tile(pl, tile);
                 if (PAIR) tc.co_tile = tc.co_tile * 2 + rank;
@@ -143,15 +148,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                         {
                             const int s = b_it & 1; const uint32_t ph = (b_it >> 1) & 1;
                             mbar_wait(emptyB + s, ph ^ 1);
-                            uint8_t* dst = b_base + (size_t)s * planes * bPlane;
+                            uint8_t* dst = b_base + (size_t)s * b_planes * bPlane;
                             if (PAIR) {
                                 if (rank == 0) mbar_expect_tx(fullB + s, 2 * b_bytes);     // both CTAs' halves
                                 tma_load_4d_pair(dst, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
-                                if (three) tma_load_4d_pair(dst + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
+                                if (x_lo) tma_load_4d_pair(dst + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
                             } else {
                                 mbar_expect_tx(fullB + s, b_bytes);
                                 tma_load_4d(dst, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
-                                if (three) tma_load_4d(dst + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
+                                if (x_lo) tma_load_4d(dst + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
                             }
                             ++b_it;
                         }
@@ -161,7 +166,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                             mbar_wait(emptyA + s, ph ^ 1);
                             if (!PAIR) mbar_expect_tx(fullA + s, a_bytes);
                             else if (rank == 0) mbar_expect_tx(fullA + s, 2 * a_bytes);
-                            uint8_t* dst = a_base + (size_t)s * planes * kATileBytes;
+                            uint8_t* dst = a_base + (size_t)s * a_planes * kATileBytes;
                             auto load_w = [&](uint8_t* d, const CUtensorMap* m, int c0, int c1) {
                                 if (PAIR) tma_load_3d_pair(d, m, fullA + s, c0, c1, tp.w_idx);
                                 else tma_load_3d(d, m, fullA + s, c0, c1, tp.w_idx);
@@ -169,11 +174,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                             if (prm.a_mn) {     // two {64 co, 64 ci-rows} boxes: MN-major atom stacks, 8 KB apart
                                 for (int h = 0; h < 2; ++h) {
                                     load_w(dst + h * 8192, &map_w_hi, tc.co_tile * 128 + h * 64, ch * 64);
-                                    if (three) load_w(dst + kATileBytes + h * 8192, &map_w_lo, tc.co_tile * 128 + h * 64, ch * 64);
+                                    if (w_lo) load_w(dst + kATileBytes + h * 8192, &map_w_lo, tc.co_tile * 128 + h * 64, ch * 64);
                                 }
                             } else {
                                 load_w(dst, &map_w_hi, ch * 64, tc.co_tile * 128);
-                                if (three) load_w(dst + kATileBytes, &map_w_lo, ch * 64, tc.co_tile * 128);
+                                if (w_lo) load_w(dst + kATileBytes, &map_w_lo, ch * 64, tc.co_tile * 128);
                             }
                             ++a_it;
                         }
@@ -183,14 +188,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
         }
     } else if (warp == 1) {
         // ======================================================================= MMA issuer
-        if (lane == 0 && rank == 0) {
+        // The whole warp runs this loop with warp-uniform control flow; only the tcgen05 instructions
+        // themselves are issued by one elected lane (always the same one, so tcgen05.commit tracks them).
+        if (rank == 0) {
             uint32_t a_it = 0, b_it = 0, t_it = 0;
-            const uint32_t idesc = make_idesc_bf16(pl.n_tile, PAIR ? 256 : 128) | (prm.a_mn ? (1u << 15) : 0u);
+            // operand format field: 1 = bf16, 0 = fp16 (bits [7,10) for A, [10,13) for B)
+            const uint32_t idesc = (make_idesc_bf16(pl.n_tile, PAIR ? 256 : 128) & ~(prm.f16 ? ((7u << 7) | (7u << 10)) : 0u)) |
+                                   (prm.a_mn ? (1u << 15) : 0u);
             const bool a_mn = prm.a_mn != 0;
             auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc_flag) {
-                if (PAIR) umma_bf16_pair(d, da, db, idesc, acc_flag); else umma_bf16(d, da, db, idesc, acc_flag);
+                if (elect_one()) { if (PAIR) umma_bf16_pair(d, da, db, idesc, acc_flag); else umma_bf16(d, da, db, idesc, acc_flag); }
             };
-            auto commit = [&](uint64_t* bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
+            auto commit = [&](uint64_t* bar) {
+                if (elect_one()) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); }
+                __syncwarp();
+            };
             for (int tile = tile0; tile < n_tiles; tile += tile_step, ++t_it) {
                 TileCoord tc = decode_tile(pl, tile);
                 const int acc = pl.acc_stages == 2 ? (t_it & 1) : 0;
@@ -207,14 +219,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                         const int bs = b_it & 1; const uint32_t bph = (b_it >> 1) & 1;
                         mbar_wait(fullB + bs, bph);
                         tc_fence_after();
-                        const uint32_t b_hi = smem_u32(b_base + (size_t)bs * planes * bPlane);
+                        const uint32_t b_hi = smem_u32(b_base + (size_t)bs * b_planes * bPlane);
                         const uint32_t b_lo = b_hi + bPlane;
                         for (int j = 0; j < grp.n_taps; ++j) {
                             const ConvTap tp = pl.taps[tc.phase][grp.first_tap + j];
                             const int as = a_it % nA; const uint32_t aph = (a_it / nA) & 1;
                             mbar_wait(fullA + as, aph);
                             tc_fence_after();
-                            const uint32_t a_hi = smem_u32(a_base + (size_t)as * planes * kATileBytes);
+                            const uint32_t a_hi = smem_u32(a_base + (size_t)as * a_planes * kATileBytes);
                             const uint32_t a_lo = a_hi + kATileBytes;
                             const uint32_t sh = (uint32_t)tp.shift * 128u;
                             for (int c = 0; c < pl.nb; ++c) {      // one MMA group per clip of the bundle
@@ -225,11 +237,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                                 for (int kk = 0; kk < 4; ++kk) {   // 4 x (K = 16) per 64-channel chunk
                                     const uint64_t da_hi = a_mn ? make_desc_sw128_mn(a_hi + kk * 2048, 8192) : make_desc_sw128(a_hi + kk * 32, 0);
                                     const uint64_t db_hi = make_desc_sw128(b_hi + boff + kk * 32, prm.base_offset_mode);
-                                    if (three) {
+                                    if (w_lo) {
                                         const uint64_t da_lo = a_mn ? make_desc_sw128_mn(a_lo + kk * 2048, 8192) : make_desc_sw128(a_lo + kk * 32, 0);
                                         const uint64_t db_lo = make_desc_sw128(b_lo + boff + kk * 32, prm.base_offset_mode);
                                         mma(dcol, da_lo, db_hi, kk == 0 ? acc_c : 1u);
                                         mma(dcol, da_hi, db_lo, 1);
+                                        mma(dcol, da_hi, db_hi, 1);
+                                    } else if (x_lo) {
+                                        const uint64_t db_lo = make_desc_sw128(b_lo + boff + kk * 32, prm.base_offset_mode);
+                                        mma(dcol, da_hi, db_lo, kk == 0 ? acc_c : 1u);
                                         mma(dcol, da_hi, db_hi, 1);
                                     } else {
                                         mma(dcol, da_hi, db_hi, kk == 0 ? acc_c : 1u);
@@ -350,9 +366,11 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
                           const uint16_t* w_lo, float* y, float* stats, pg_stream stream) {
     using namespace pg;
     PG_REQUIRE(d && x_hi && w_hi && y, "pg_conv_tc: null pointer");
-    PG_REQUIRE(d->precision == PG_PREC_BF16X3 || d->precision == PG_PREC_BF16, "pg_conv_tc: precision must be BF16X3 or BF16");
-    const bool three = d->precision == PG_PREC_BF16X3;
-    PG_REQUIRE(!three || (x_lo && w_lo), "pg_conv_tc: lo planes required for BF16X3");
+    PG_REQUIRE(d->precision >= PG_PREC_BF16X3 && d->precision <= PG_PREC_F16X2, "pg_conv_tc: precision must be BF16X3, BF16, F16X3 or F16X2");
+    const int n_terms = (d->precision == PG_PREC_BF16X3 || d->precision == PG_PREC_F16X3) ? 3 : d->precision == PG_PREC_F16X2 ? 2 : 1;
+    const bool three = n_terms == 3;
+    PG_REQUIRE(n_terms < 3 || w_lo, "pg_conv_tc: weight lo plane required for the three-product precisions");
+    PG_REQUIRE(n_terms < 2 || x_lo, "pg_conv_tc: activation lo plane required for this precision");
     PG_REQUIRE(d->C_in % 64 == 0 && d->C_out % 128 == 0, "pg_conv_tc: needs C_in %% 64 == 0 and C_out %% 128 == 0 (got %d, %d)", d->C_in, d->C_out);
     PG_REQUIRE(d->in_ld % 8 == 0, "pg_conv_tc: input row pitch must be a multiple of 8 elements");
     ConvTcParams prm;
@@ -364,17 +382,18 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     const ConvPlan& pl = prm.plan;
     { int a_, b_; device_limits(&a_, &b_); }
     prm.y = y; prm.stats = reinterpret_cast<float4*>(stats);
-    prm.n_terms = three ? 3 : 1;
+    prm.n_terms = n_terms;
+    prm.f16 = (d->precision == PG_PREC_F16X3 || d->precision == PG_PREC_F16X2) ? 1 : 0;
     prm.base_offset_mode = d->tc_base_offset_mode;
     prm.a_mn = d->weights_mn_major ? 1 : 0;
     prm.b_slot_bytes = pl.nb * pl.strip_rows * 128;
-    const int planes = three ? 2 : 1;
-    const int fixed = 2 * planes * prm.b_slot_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
-    int nA = (g_max_smem - fixed) / (planes * kATileBytes);
+    const int a_planes = n_terms == 3 ? 2 : 1, b_planes = n_terms >= 2 ? 2 : 1;
+    const int fixed = 2 * b_planes * prm.b_slot_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    int nA = (g_max_smem - fixed) / (a_planes * kATileBytes);
     if (nA > kMaxASlots) nA = kMaxASlots;
     PG_REQUIRE(nA >= 2, "pg_conv_tc: strip of %d rows leaves no room for the weight ring", pl.strip_rows);
     prm.n_a_slots = nA;
-    const size_t smem_bytes = (size_t)fixed + (size_t)nA * planes * kATileBytes;
+    const size_t smem_bytes = (size_t)fixed + (size_t)nA * a_planes * kATileBytes;
 
     CUtensorMap mw_hi, mw_lo, mx_hi, mx_lo;
     {
@@ -395,7 +414,7 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
         uint32_t box[4] = {64, 1, (uint32_t)pl.strip_rows, (uint32_t)pl.nb};
         PG_REQUIRE(d->in_rows >= ((d->L_in + IS - 1) / IS) * IS, "pg_conv_tc: in_rows %d too small for L_in %d at stride %d", d->in_rows, d->L_in, IS);
         if ((rc = encode_bf16_map(&mx_hi, x_hi, 4, dims, str, box, "x_hi")) != PG_OK) return rc;
-        if ((rc = encode_bf16_map(&mx_lo, three ? x_lo : x_hi, 4, dims, str, box, "x_lo")) != PG_OK) return rc;
+        if ((rc = encode_bf16_map(&mx_lo, n_terms >= 2 ? x_lo : x_hi, 4, dims, str, box, "x_lo")) != PG_OK) return rc;
     }
     const bool pair = pl.pair != 0;
     {
@@ -410,7 +429,7 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     {
         // clips per L2-resident group: keep ~64 MB of activations hot while every weight slab passes over them
         const int nbg = (pl.B + pl.nb - 1) / pl.nb;
-        const double bundle_bytes = (double)pl.nb * d->in_rows * d->in_ld * (three ? 4.0 : 2.0);
+        const double bundle_bytes = (double)pl.nb * d->in_rows * d->in_ld * (n_terms >= 2 ? 4.0 : 2.0);
         int G = (int)(64.0e6 / bundle_bytes);
         if (const char* e = getenv("PG_TC_CLIP_GROUP")) G = atoi(e);   // test hook: force small groups
         if (G < 1) G = 1;

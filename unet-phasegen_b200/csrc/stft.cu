@@ -111,8 +111,8 @@ template <int NC, int FR>
 __global__ void __launch_bounds__(StftCfg<NC, FR>::THREADS)
 stft_kernel(const float* __restrict__ wave, int N, int T, const float2* __restrict__ tw_g, int mode,
             float* __restrict__ out_a, float* __restrict__ out_b,
-            __nv_bfloat16* __restrict__ op_hi, __nv_bfloat16* __restrict__ op_lo,
-            long long op_batch_stride) {
+            uint16_t* __restrict__ op_hi, uint16_t* __restrict__ op_lo,
+            long long op_batch_stride, int op_fmt) {
     using Cfg = StftCfg<NC, FR>;
     extern __shared__ float smem[];
     cpx* tw = reinterpret_cast<cpx*>(smem);                 // [NFFT] exp(-2 pi i m / n_fft)
@@ -170,8 +170,8 @@ stft_kernel(const float* __restrict__ wave, int N, int T, const float2* __restri
         if (out_a) out_a[o_idx] = a;
         if (out_b) out_b[o_idx] = ph;
         if (op_hi) {
-            __nv_bfloat16 hi, lo;
-            split_bf16(a, hi, lo);
+            uint16_t hi, lo;
+            split16(a, op_fmt, hi, lo);
             size_t q = (size_t)b * op_batch_stride + (size_t)frame * NC + (k - 1);
             op_hi[q] = hi;
             if (op_lo) op_lo[q] = lo;
@@ -309,15 +309,14 @@ template <int NC> struct FramesPerCta {
 
 template <int NC>
 static int launch_stft(const float* wave, int B, int N, int T, const float* tw, int mode, float* a, float* bq,
-                       uint16_t* hi, uint16_t* lo, long long bs, cudaStream_t st) {
+                       uint16_t* hi, uint16_t* lo, long long bs, int fmt, cudaStream_t st) {
     constexpr int FR = FramesPerCta<NC>::STFT;
     using Cfg = StftCfg<NC, FR>;
     auto k = stft_kernel<NC, FR>;
     size_t sm = Cfg::smem_stft();
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     dim3 grid((T + Cfg::FR - 1) / Cfg::FR, B);
-    k<<<grid, Cfg::THREADS, sm, st>>>(wave, N, T, reinterpret_cast<const float2*>(tw), mode, a, bq,
-                                     reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), bs);
+    k<<<grid, Cfg::THREADS, sm, st>>>(wave, N, T, reinterpret_cast<const float2*>(tw), mode, a, bq, hi, lo, bs, fmt);
     return check_launch("stft_kernel");
 }
 
@@ -342,7 +341,7 @@ extern "C" int pg_stft_num_frames(int n_samples, int hop) { return hop > 0 ? 1 +
 
 extern "C" int pg_stft(const float* wave, int B, int N, int n_fft, int hop, const float* twiddle, int mode,
                        float* out_a, float* out_b, uint16_t* op_hi, uint16_t* op_lo,
-                       int64_t op_batch_stride, pg_stream stream) {
+                       int64_t op_batch_stride, int op_fmt, pg_stream stream) {
     PG_REQUIRE(wave && twiddle && B > 0 && N > 0, "pg_stft: null pointer or empty batch");
     PG_REQUIRE(hop * 4 == n_fft, "pg_stft: hop must be n_fft/4 (got n_fft=%d hop=%d)", n_fft, hop);
     PG_REQUIRE(N > n_fft / 2, "pg_stft: reflect padding needs more than n_fft/2 samples (N=%d)", N);
@@ -351,10 +350,10 @@ extern "C" int pg_stft(const float* wave, int B, int N, int n_fft, int hop, cons
     const int T = 1 + N / hop;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (n_fft) {
-        case 256:  return pg::launch_stft<128>(wave, B, N, T, twiddle, mode, out_a, out_b, op_hi, op_lo, op_batch_stride, st);
-        case 512:  return pg::launch_stft<256>(wave, B, N, T, twiddle, mode, out_a, out_b, op_hi, op_lo, op_batch_stride, st);
-        case 1024: return pg::launch_stft<512>(wave, B, N, T, twiddle, mode, out_a, out_b, op_hi, op_lo, op_batch_stride, st);
-        case 2048: return pg::launch_stft<1024>(wave, B, N, T, twiddle, mode, out_a, out_b, op_hi, op_lo, op_batch_stride, st);
+        case 256:  return pg::launch_stft<128>(wave, B, N, T, twiddle, mode, out_a, out_b, op_hi, op_lo, op_batch_stride, op_fmt, st);
+        case 512:  return pg::launch_stft<256>(wave, B, N, T, twiddle, mode, out_a, out_b, op_hi, op_lo, op_batch_stride, op_fmt, st);
+        case 1024: return pg::launch_stft<512>(wave, B, N, T, twiddle, mode, out_a, out_b, op_hi, op_lo, op_batch_stride, op_fmt, st);
+        case 2048: return pg::launch_stft<1024>(wave, B, N, T, twiddle, mode, out_a, out_b, op_hi, op_lo, op_batch_stride, op_fmt, st);
     }
     pg::set_error("pg_stft: n_fft must be 256, 512, 1024 or 2048 (got %d)", n_fft);
     return PG_ERR_UNSUPPORTED;

@@ -106,11 +106,12 @@ __device__ __forceinline__ void store_act4(const ActDst& d, int b, int l, int c,
     if (d.dtype == PG_DT_F32) {
         *reinterpret_cast<float4*>(static_cast<float*>(d.hi) + o) = v;
     } else {
-        __nv_bfloat16 h[4], lo[4];
-        split_bf16(v.x, h[0], lo[0]); split_bf16(v.y, h[1], lo[1]);
-        split_bf16(v.z, h[2], lo[2]); split_bf16(v.w, h[3], lo[3]);
-        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(d.hi) + o) = *reinterpret_cast<uint2*>(h);
-        if (d.dtype == PG_DT_BF16_SPLIT) *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(d.lo) + o) = *reinterpret_cast<uint2*>(lo);
+        __align__(8) uint16_t h[4], lo[4];
+        const int fmt = fmt_of_dtype(d.dtype);
+        split16(v.x, fmt, h[0], lo[0]); split16(v.y, fmt, h[1], lo[1]);
+        split16(v.z, fmt, h[2], lo[2]); split16(v.w, fmt, h[3], lo[3]);
+        *reinterpret_cast<uint2*>(static_cast<uint16_t*>(d.hi) + o) = *reinterpret_cast<uint2*>(h);
+        if (d.dtype == PG_DT_BF16_SPLIT || d.dtype == PG_DT_F16_SPLIT) *reinterpret_cast<uint2*>(static_cast<uint16_t*>(d.lo) + o) = *reinterpret_cast<uint2*>(lo);
     }
 }
 
@@ -137,7 +138,7 @@ bn_act_kernel(const float* __restrict__ y, int L, int C, int rows, int ld, const
 
 // --------------------------------------------------------------------------- weight pack
 __global__ void pack_weight_kernel(const float* __restrict__ w, int transposed, int C_in, int C_out, int k,
-                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ simt) {
+                                   uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, float* __restrict__ simt, int fmt) {
     const size_t total = (size_t)k * C_out * C_in;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int ci = (int)(i % C_in);
@@ -146,8 +147,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int transposed, 
         // Conv1d weight [C_out][C_in][k]; ConvTranspose1d weight [C_in][C_out][k]
         const float v = transposed ? w[((size_t)ci * C_out + co) * k + t] : w[((size_t)co * C_in + ci) * k + t];
         if (hi) {
-            __nv_bfloat16 h, l;
-            split_bf16(v, h, l);
+            uint16_t h, l;
+            split16(v, fmt, h, l);
             hi[i] = h;
             if (lo) lo[i] = l;
         }
@@ -157,11 +158,11 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int transposed, 
 
 // ------------------------------------------------------------------------------ cast/split
 __global__ void __launch_bounds__(256)
-cast_split_kernel(const float* __restrict__ src, size_t n4, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+cast_split_kernel(const float* __restrict__ src, size_t n4, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int fmt) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const float4 v = reinterpret_cast<const float4*>(src)[i];
-        __nv_bfloat16 h[4], l[4];
-        split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+        __align__(8) uint16_t h[4], l[4];
+        split16(v.x, fmt, h[0], l[0]); split16(v.y, fmt, h[1], l[1]); split16(v.z, fmt, h[2], l[2]); split16(v.w, fmt, h[3], l[3]);
         reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
         if (lo) reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
     }
@@ -169,8 +170,8 @@ cast_split_kernel(const float* __restrict__ src, size_t n4, __nv_bfloat16* __res
 
 // ----------------------------------------------------------------------------- transpose
 __global__ void transpose_kernel(const float* __restrict__ src, int R, int S, long long src_batch_stride,
-                                 float* __restrict__ dst, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                 long long dst_batch_stride, int dst_ld) {
+                                 float* __restrict__ dst, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                 long long dst_batch_stride, int dst_ld, int fmt) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -187,8 +188,8 @@ __global__ void transpose_kernel(const float* __restrict__ src, int R, int S, lo
             const size_t o = (size_t)b * dst_batch_stride + (size_t)s * dst_ld + r;
             if (dst) dst[o] = v;
             if (hi) {
-                __nv_bfloat16 h, l;
-                split_bf16(v, h, l);
+                uint16_t h, l;
+                split16(v, fmt, h, l);
                 hi[o] = h;
                 if (lo) lo[o] = l;
             }
@@ -236,8 +237,8 @@ extern "C" int pg_bn_finalize(const float* stats, int B, int P, int C, int per_c
 static int to_dst(const pg_act_dst* s, int C, ActDst* o, const char* which) {
     o->dtype = 0; o->hi = o->lo = nullptr; o->batch_stride = 0; o->ld = 0; o->ch_off = 0; o->slope = 1.f;
     if (!s || s->dtype == PG_DT_NONE) return PG_OK;
-    PG_REQUIRE(s->dtype == PG_DT_F32 || s->dtype == PG_DT_BF16_SPLIT || s->dtype == PG_DT_BF16, "pg_bn_act: %s: bad dtype %d", which, s->dtype);
-    PG_REQUIRE(s->hi && (s->dtype != PG_DT_BF16_SPLIT || s->lo), "pg_bn_act: %s: null plane", which);
+    PG_REQUIRE(s->dtype >= PG_DT_F32 && s->dtype <= PG_DT_F16, "pg_bn_act: %s: bad dtype %d", which, s->dtype);
+    PG_REQUIRE(s->hi && ((s->dtype != PG_DT_BF16_SPLIT && s->dtype != PG_DT_F16_SPLIT) || s->lo), "pg_bn_act: %s: null plane", which);
     PG_REQUIRE(s->ld % 4 == 0 && s->ch_off % 4 == 0 && s->batch_stride % 4 == 0 && s->ch_off + C <= s->ld, "pg_bn_act: %s: misaligned or too narrow destination", which);
     o->hi = s->hi; o->lo = s->lo; o->batch_stride = s->batch_stride; o->ld = s->ld; o->ch_off = s->ch_off; o->dtype = s->dtype; o->slope = s->slope;
     return PG_OK;
@@ -259,31 +260,30 @@ extern "C" int pg_bn_act(const float* y, int B, int L, int C, int rows, int ld, 
 }
 
 extern "C" int pg_pack_weight(const float* w, int kind, int C_in, int C_out, int k, uint16_t* w_hi, uint16_t* w_lo,
-                              float* w_simt, pg_stream stream) {
+                              float* w_simt, int fmt, pg_stream stream) {
     PG_REQUIRE(w && (w_hi || w_simt) && C_in > 0 && C_out > 0 && k > 0, "pg_pack_weight: bad arguments");
+    PG_REQUIRE(fmt == PG_FMT_BF16 || fmt == PG_FMT_F16, "pg_pack_weight: bad operand format %d", fmt);
     const size_t total = (size_t)k * C_out * C_in;
     int gx = (int)((total + 255) / 256); if (gx > 148 * 16) gx = 148 * 16;
     pack_weight_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        w, kind == PG_CONV_TRANSPOSE, C_in, C_out, k, reinterpret_cast<__nv_bfloat16*>(w_hi),
-        reinterpret_cast<__nv_bfloat16*>(w_lo), w_simt);
+        w, kind == PG_CONV_TRANSPOSE, C_in, C_out, k, w_hi, w_lo, w_simt, fmt);
     return check_launch("pack_weight_kernel");
 }
 
-extern "C" int pg_cast_split(const float* src, int64_t n, uint16_t* hi, uint16_t* lo, pg_stream stream) {
+extern "C" int pg_cast_split(const float* src, int64_t n, uint16_t* hi, uint16_t* lo, int fmt, pg_stream stream) {
     PG_REQUIRE(src && hi && n > 0 && n % 4 == 0, "pg_cast_split: bad arguments (n must be a multiple of 4)");
+    PG_REQUIRE(fmt == PG_FMT_BF16 || fmt == PG_FMT_F16, "pg_cast_split: bad operand format %d", fmt);
     const size_t n4 = (size_t)n / 4;
     int gx = (int)((n4 + 255) / 256); if (gx > 148 * 32) gx = 148 * 32;
-    cast_split_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, n4, reinterpret_cast<__nv_bfloat16*>(hi),
-                                                                             reinterpret_cast<__nv_bfloat16*>(lo));
+    cast_split_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, n4, hi, lo, fmt);
     return check_launch("cast_split_kernel");
 }
 
 extern "C" int pg_transpose(const float* src, int B, int R, int S, int64_t src_batch_stride, float* dst, uint16_t* dst_hi,
-                            uint16_t* dst_lo, int64_t dst_batch_stride, int dst_ld, pg_stream stream) {
+                            uint16_t* dst_lo, int64_t dst_batch_stride, int dst_ld, int fmt, pg_stream stream) {
     PG_REQUIRE(src && (dst || dst_hi) && B > 0 && R > 0 && S > 0 && B <= 65535 && dst_ld >= R, "pg_transpose: bad arguments");
     dim3 grid((S + 31) / 32, (R + 31) / 32, B);
     transpose_kernel<<<grid, dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        src, R, S, src_batch_stride, dst, reinterpret_cast<__nv_bfloat16*>(dst_hi), reinterpret_cast<__nv_bfloat16*>(dst_lo),
-        dst_batch_stride, dst_ld);
+        src, R, S, src_batch_stride, dst, dst_hi, dst_lo, dst_batch_stride, dst_ld, fmt);
     return check_launch("transpose_kernel");
 }

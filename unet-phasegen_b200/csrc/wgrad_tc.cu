@@ -63,7 +63,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
     uint64_t* accEmpty = accFull + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accEmpty + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // shuffled warp index: provably warp-uniform role branches (see conv_tc.cu)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int n_groups = pl.n_groups[0] + pl.n_groups[1];
     const int n_items = pl.n_cotiles * (pl.C_in / prm.nci) * n_groups;
     const int n_kchunks = pl.B * prm.n_mchunks;
@@ -78,7 +79,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -108,9 +109,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp, warp-uniform control flow; one elected lane issues the tcgen05 instructions
             uint32_t it = 0, n_it = 0;
             const uint32_t idesc = make_idesc_bf16_mn(prm.nci);
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc_flag) { if (elect_one()) umma_bf16(d, da, db, idesc, acc_flag); };
+            auto commit = [&](uint64_t* bar) { if (elect_one()) umma_commit(bar); __syncwarp(); };
             const uint32_t lbo_a = (uint32_t)prm.R * 128u, lbo_b = (uint32_t)prm.RB * 128u;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_it) {
                 const WgItem w = wg_decode(prm, item);
@@ -135,17 +138,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
                             if (three) {
                                 const uint64_t da_lo = make_desc_sw128_mn(a_lo + ao, lbo_a);
                                 const uint64_t db_lo = make_desc_sw128_mn(b_lo + bo, lbo_b);
-                                umma_bf16(d_tmem, da_lo, db_hi, idesc, acc);
-                                umma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
-                                umma_bf16(d_tmem, da_hi, db_hi, idesc, 1);
+                                mma(d_tmem, da_lo, db_hi, acc);
+                                mma(d_tmem, da_hi, db_lo, 1);
+                                mma(d_tmem, da_hi, db_hi, 1);
                             } else {
-                                umma_bf16(d_tmem, da_hi, db_hi, idesc, acc);
+                                mma(d_tmem, da_hi, db_hi, acc);
                             }
                         }
                     }
-                    umma_commit(empty + s);
+                    commit(empty + s);
                 }
-                umma_commit(accFull);
+                commit(accFull);
             }
         }
     } else {

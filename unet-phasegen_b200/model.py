@@ -131,7 +131,9 @@ class _UNetFunction(torch.autograd.Function):
 
 
 class UNetModel(nn.Module):
-    precision = "auto"     # "auto" | "bf16x3" (fp32-class, 3 bf16 tensor-core products) | "bf16" | "fp32_simt"
+    # "auto" | "bf16x3" (fp32-class, 3 bf16 tensor-core products) | "f16x3" (same on fp16 planes) | "f16mix"
+    # (f16x3 with the two-product form on d1/u1/u2) | "f16x2" | "bf16" | "fp32_simt"
+    precision = "auto"
     train_precision = "auto"   # precision of forward+backward under autograd (same choices)
     phase_only = False     # compute only out[:, :C] of the last layer (what demo.py:38 / train.py:78 use)
 
@@ -186,6 +188,8 @@ class UNetModel(nn.Module):
         from phasegen.train import TrainExecutor
         levels = self._levels()
         prec = precision or (self.train_precision if self.train_precision != "auto" else self._resolve_precision(levels))
+        if prec.startswith("f16"):
+            prec = "bf16x3"     # the fp16 operand modes are inference-only; autograd runs the bf16 fp32-class form
         key = ("train", B, T, str(device), prec)
         ex = self._exec.get(key)
         if ex is None:

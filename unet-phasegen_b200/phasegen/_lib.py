@@ -10,12 +10,16 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "..", "csrc", "libphasegen.so")
 
 PG_CONV, PG_CONV_TRANSPOSE = 0, 1
-PG_PREC_FP32_SIMT, PG_PREC_BF16X3, PG_PREC_BF16 = 0, 1, 2
-PG_DT_NONE, PG_DT_F32, PG_DT_BF16_SPLIT, PG_DT_BF16 = 0, 1, 2, 3
+PG_PREC_FP32_SIMT, PG_PREC_BF16X3, PG_PREC_BF16, PG_PREC_F16X3, PG_PREC_F16X2 = 0, 1, 2, 3, 4
+PG_DT_NONE, PG_DT_F32, PG_DT_BF16_SPLIT, PG_DT_BF16, PG_DT_F16_SPLIT, PG_DT_F16 = 0, 1, 2, 3, 4, 5
+PG_FMT_BF16, PG_FMT_F16 = 0, 1
 PG_STFT_LOGMAG, PG_STFT_REIM = 0, 1
 PG_SPEC_POLAR_LOG, PG_SPEC_CARTESIAN, PG_SPEC_POLAR_MAG = 0, 1, 2
 
-PRECISIONS = {"fp32_simt": PG_PREC_FP32_SIMT, "bf16x3": PG_PREC_BF16X3, "bf16": PG_PREC_BF16}
+# "f16mix" is an executor-level name (phasegen/unet.py): fp16 planes everywhere, the three-product
+# form on the small layers and the two-product form (fp16-rounded weights) on the three largest.
+PRECISIONS = {"fp32_simt": PG_PREC_FP32_SIMT, "bf16x3": PG_PREC_BF16X3, "bf16": PG_PREC_BF16,
+              "f16x3": PG_PREC_F16X3, "f16x2": PG_PREC_F16X2}
 
 
 class ConvDesc(C.Structure):
@@ -40,24 +44,24 @@ _SIGNATURES = {
     "pg_abi_version": (_I, []),
     "pg_check_device": (_I, [C.POINTER(_I)] * 3),
     "pg_stft_num_frames": (_I, [_I, _I]),
-    "pg_stft": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _L, _P]),
+    "pg_stft": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _L, _I, _P]),
     "pg_istft": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "pg_peak_normalize": (_I, [_P, _P, _I, _I, _P]),
-    "pg_pack_weight": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "pg_pack_weight": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "pg_conv_tc": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "pg_conv_stat_parts": (_I, [C.POINTER(ConvDesc)]),
     "pg_conv_simt": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P]),
     "pg_channel_stats": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "pg_bn_finalize": (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _P, _P, _P]),
     "pg_bn_act": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, C.POINTER(ActDst), C.POINTER(ActDst), _P]),
-    "pg_transpose": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _L, _I, _P]),
+    "pg_transpose": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _L, _I, _I, _P]),
     "pg_phase_loss": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _I, _P, _P]),
     "pg_bn_bwd": (_I, [_P, _I, _I, _I, _P, _P, _F, C.POINTER(GradSrc), C.POINTER(GradSrc), _P, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
     "pg_wgrad_tc": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _I, _P, _P]),
     "pg_wgrad_simt": (_I, [C.POINTER(ConvDesc), _P, _P, _I, _P, _P]),
     "pg_unpack_grad": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "pg_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P, _P, _P]),
-    "pg_cast_split": (_I, [_P, _L, _P, _P, _P]),
+    "pg_cast_split": (_I, [_P, _L, _P, _P, _I, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -6,9 +6,10 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (ActDst, ConvDesc, PG_CONV, PG_CONV_TRANSPOSE, PG_DT_BF16, PG_DT_BF16_SPLIT, PG_DT_F32,
-                   PG_DT_NONE, PG_PREC_BF16, PG_PREC_BF16X3, PG_PREC_FP32_SIMT, PG_SPEC_CARTESIAN,
-                   PG_SPEC_POLAR_LOG, PG_SPEC_POLAR_MAG, PG_STFT_LOGMAG, PG_STFT_REIM)
+from ._lib import (ActDst, ConvDesc, PG_CONV, PG_CONV_TRANSPOSE, PG_DT_BF16, PG_DT_BF16_SPLIT, PG_DT_F16,
+                   PG_DT_F16_SPLIT, PG_DT_F32, PG_DT_NONE, PG_FMT_BF16, PG_FMT_F16, PG_PREC_BF16, PG_PREC_BF16X3,
+                   PG_PREC_F16X2, PG_PREC_F16X3, PG_PREC_FP32_SIMT, PG_SPEC_CARTESIAN, PG_SPEC_POLAR_LOG,
+                   PG_SPEC_POLAR_MAG, PG_STFT_LOGMAG, PG_STFT_REIM)
 
 SUPPORTED_N_FFT = (256, 512, 1024, 2048)
 
@@ -19,6 +20,15 @@ def _stream():
 
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _fmt(t):
+    """16-bit operand format of a plane tensor (None -> bf16)."""
+    if t is None or t.dtype == torch.bfloat16:
+        return PG_FMT_BF16
+    if t.dtype == torch.float16:
+        return PG_FMT_F16
+    raise RuntimeError(f"phasegen: operand planes must be bfloat16 or float16, got {t.dtype}")
 
 
 def _need_cuda(t, name, dtype=torch.float32):
@@ -64,7 +74,7 @@ def stft(wave, n_fft, hop, mode=PG_STFT_LOGMAG, want_second=True, operand=None):
     b = torch.empty_like(a) if want_second else None
     hi, lo, bs = operand if operand is not None else (None, None, 0)
     _lib.call("pg_stft", _ptr(wave), B, N, n_fft, hop, _ptr(twiddle(n_fft, wave.device)), mode,
-              _ptr(a), _ptr(b), _ptr(hi), _ptr(lo), bs, _stream())
+              _ptr(a), _ptr(b), _ptr(hi), _ptr(lo), bs, _fmt(hi), _stream())
     return a, b
 
 
@@ -98,7 +108,7 @@ def transpose(src, dst=None, dst_hi=None, dst_lo=None, dst_batch_stride=None, ds
         dst = torch.empty(B, S, R, device=src.device, dtype=torch.float32)
     ld = R if dst_ld is None else dst_ld
     bs = S * ld if dst_batch_stride is None else dst_batch_stride
-    _lib.call("pg_transpose", _ptr(src), B, R, S, R * S, _ptr(dst), _ptr(dst_hi), _ptr(dst_lo), bs, ld, _stream())
+    _lib.call("pg_transpose", _ptr(src), B, R, S, R * S, _ptr(dst), _ptr(dst_hi), _ptr(dst_lo), bs, ld, _fmt(dst_hi), _stream())
     return dst
 
 
@@ -111,7 +121,7 @@ def conv_desc(kind, B, C_in, C_out, L_in, k, stride, pad, in_rows, in_ld, precis
                     precision, taps_per_group, base_offset_mode, max_ctas, max_clips_per_tile, weights_mn_major, cta_pair)
 
 
-def pack_weight(w, kind, want_tc=True, want_simt=False):
+def pack_weight(w, kind, want_tc=True, want_simt=False, plane_dtype=torch.bfloat16, want_lo=True):
     """torch Conv1d [C_out,C_in,k] / ConvTranspose1d [C_in,C_out,k] weight -> kernel layouts."""
     w = _need_cuda(w.detach(), "weight")
     if kind == PG_CONV_TRANSPOSE:
@@ -120,11 +130,11 @@ def pack_weight(w, kind, want_tc=True, want_simt=False):
         C_out, C_in, k = w.shape
     hi = lo = simt = None
     if want_tc:
-        hi = torch.empty(k, C_out, C_in, device=w.device, dtype=torch.bfloat16)
-        lo = torch.empty_like(hi)
+        hi = torch.empty(k, C_out, C_in, device=w.device, dtype=plane_dtype)
+        lo = torch.empty_like(hi) if want_lo else None
     if want_simt:
         simt = torch.empty(k, C_in, C_out, device=w.device, dtype=torch.float32)
-    _lib.call("pg_pack_weight", _ptr(w), kind, C_in, C_out, k, _ptr(hi), _ptr(lo), _ptr(simt), _stream())
+    _lib.call("pg_pack_weight", _ptr(w), kind, C_in, C_out, k, _ptr(hi), _ptr(lo), _ptr(simt), _fmt(hi), _stream())
     return hi, lo, simt
 
 
@@ -200,8 +210,8 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0, w_hi=None
 
 
 def cast_split(src, hi, lo=None):
-    """fp32 (contiguous) -> bf16 hi(/lo) planes of the same element order."""
-    _lib.call("pg_cast_split", _ptr(src), src.numel(), _ptr(hi), _ptr(lo), _stream())
+    """fp32 (contiguous) -> bf16 or fp16 hi(/lo) planes of the same element order."""
+    _lib.call("pg_cast_split", _ptr(src), src.numel(), _ptr(hi), _ptr(lo), _fmt(hi), _stream())
 
 
 def packed_view(weight, kind):

@@ -8,7 +8,7 @@ numpy/CPU round trips the reference makes at demo.py:37-40.
 import torch
 
 from . import ops
-from ._lib import PG_SPEC_POLAR_LOG, PG_STFT_LOGMAG
+from ._lib import PG_DT_F32, PG_SPEC_POLAR_LOG, PG_STFT_LOGMAG
 
 
 class PhaseGenPipeline:
@@ -30,8 +30,8 @@ class PhaseGenPipeline:
         kw = {"precision": self.precision} if self.precision else {}
         ex = self.model.executor(B, T, wave.device, per_clip=self.per_clip, phase_only=self.phase_only, **kw)
         x0 = ex.x0
-        if x0.lo is not None or x0.hi.dtype == torch.bfloat16:
-            # the STFT kernel writes the first convolution's bf16 operand planes directly
+        if x0.dtype != PG_DT_F32:
+            # the STFT kernel writes the first convolution's 16-bit operand planes directly
             logmag, _ = ops.stft(wave, self.n_fft, self.hop, PG_STFT_LOGMAG, want_second=False,
                                  operand=(x0.hi, x0.lo, x0.rows * x0.ld))
         else:

@@ -14,7 +14,7 @@ upstream gradients inside one pg_bn_bwd call, each masked with its own activatio
 import torch
 
 from . import ops
-from ._lib import (PG_CONV, PG_CONV_TRANSPOSE, PG_DT_F32, PG_PREC_FP32_SIMT)
+from ._lib import (PG_CONV, PG_CONV_TRANSPOSE, PG_DT_F32, PG_PREC_BF16, PG_PREC_BF16X3, PG_PREC_FP32_SIMT)
 from .unet import UNetExecutor, _Operand, _rows
 
 N_CHUNKS = 64
@@ -23,6 +23,9 @@ N_CHUNKS = 64
 class TrainExecutor(UNetExecutor):
     def __init__(self, levels, B, T, device, precision="bf16", **kw):
         super().__init__(levels, B, T, device, precision, per_clip=False, keep_raw=True, **kw)
+        if self.prec not in (PG_PREC_FP32_SIMT, PG_PREC_BF16X3, PG_PREC_BF16):
+            raise RuntimeError("phasegen: the training step runs in 'bf16', 'bf16x3' or 'fp32_simt' "
+                               "(the fp16 operand modes are inference-only: gradients need the bf16 range)")
         D, dev, prec = self.D, self.device, self.prec
         f32 = dict(device=dev, dtype=torch.float32)
         self.d_out = torch.empty(B, self.T_out, self.C_final, **f32)

@@ -17,14 +17,21 @@ a channel offset into the up-conv's input buffer, never a copy.
 import torch
 
 from . import ops
-from ._lib import (PG_CONV, PG_CONV_TRANSPOSE, PG_DT_BF16, PG_DT_BF16_SPLIT, PG_DT_F32, PG_PREC_BF16,
-                   PG_PREC_BF16X3, PG_PREC_FP32_SIMT, PRECISIONS)
+from ._lib import (PG_CONV, PG_CONV_TRANSPOSE, PG_DT_BF16, PG_DT_BF16_SPLIT, PG_DT_F16_SPLIT, PG_DT_F32, PG_PREC_BF16,
+                   PG_PREC_BF16X3, PG_PREC_F16X2, PG_PREC_F16X3, PG_PREC_FP32_SIMT, PRECISIONS)
 
 BN_EPS_DEFAULT = 1e-5
 # Taps that share one TMA-loaded activation strip in the tensor-core kernel (1 = no strip reuse).
 # 16 with base-offset mode 0 verified on B200 against the SIMT kernel (tools/tc_probe.py,
 # profiles/r01_tc_probe.log): the UMMA swizzle is a function of the absolute smem address.
 DEFAULT_TAPS_PER_GROUP = 16
+# precision="f16mix": layers (d<level+1> / u<level+1>) that run the two-product fp16 form.  d1, u1 and
+# u2 hold 80 % of the multiply-adds of the reference U-Net; with fp16-rounded weights on
+# exactly these three the predicted phase stays within ~5e-4 relative L2 of the float64 oracle
+# (bound: 1e-3), measured in tests/test_gpu_unet.py.
+F16MIX_FAST_LAYERS = ("d1", "u1", "u2")
+_SPLIT_PRECS = (PG_PREC_BF16X3, PG_PREC_F16X3, PG_PREC_F16X2)
+_F16_PRECS = (PG_PREC_F16X3, PG_PREC_F16X2)
 DEFAULT_BASE_OFFSET_MODE = 0
 
 
@@ -65,6 +72,10 @@ class _Operand:
             self.dtype = PG_DT_F32
             self.hi = torch.zeros(B, self.rows, ld, device=device, dtype=torch.float32)
             self.lo = None
+        elif prec in _F16_PRECS:
+            self.dtype = PG_DT_F16_SPLIT
+            self.hi = torch.zeros(B, self.rows, ld, device=device, dtype=torch.float16)
+            self.lo = torch.zeros_like(self.hi)
         else:
             self.dtype = PG_DT_BF16_SPLIT if prec == PG_PREC_BF16X3 else PG_DT_BF16
             self.hi = torch.zeros(B, self.rows, ld, device=device, dtype=torch.bfloat16)
@@ -83,9 +94,13 @@ class _Operand:
 
 class UNetExecutor:
     def __init__(self, levels, B, T, device, precision="bf16x3", per_clip=False, out_channels=None,
-                 taps_per_group=None, base_offset_mode=None, keep_raw=False):
+                 taps_per_group=None, base_offset_mode=None, keep_raw=False, fast_layers=None):
         self.levels, self.B, self.T, self.device = levels, B, T, torch.device(device)
+        if precision == "f16mix":
+            precision, fast_layers = "f16x3", (F16MIX_FAST_LAYERS if fast_layers is None else fast_layers)
         self.prec = PRECISIONS[precision] if isinstance(precision, str) else precision
+        # per-layer precision: the executor's, except that fp16 executors may run named layers two-product
+        self.fast_layers = tuple(fast_layers or ()) if self.prec == PG_PREC_F16X3 else ()
         if self.prec != PG_PREC_FP32_SIMT and not tc_supported(levels):
             raise RuntimeError("phasegen: tensor-core path needs C_in % 64 == 0 and C_out % 128 == 0 in every "
                                "layer; use precision='fp32_simt' for this channel count")
@@ -130,12 +145,12 @@ class UNetExecutor:
             elif lv.up.C_in != lv.down.C_out:
                 raise RuntimeError("phasegen: innermost up conv width mismatch")
             self.dn_desc[i] = ops.conv_desc(lv.down.kind, B, lv.down.C_in, lv.down.C_out, src.L, lv.down.k,
-                                            lv.down.stride, lv.down.pad, src.rows, src.ld, prec,
+                                            lv.down.stride, lv.down.pad, src.rows, src.ld, self.layer_prec("d", i),
                                             taps_per_group=self.tpg, base_offset_mode=self.bo)
             up_src = self.a[i] if i == D - 1 else self.cat[i]
             c_out = self.C_final if i == 0 else lv.up.C_out
             self.up_desc[i] = ops.conv_desc(lv.up.kind, B, lv.up.C_in, c_out, up_src.L, lv.up.k, lv.up.stride,
-                                            lv.up.pad, up_src.rows, up_src.ld, prec,
+                                            lv.up.pad, up_src.rows, up_src.ld, self.layer_prec("u", i),
                                             taps_per_group=self.tpg, base_offset_mode=self.bo)
             self.dn_stats[i], self.dn_ss[i], self.dn_mv[i] = self._stat_bufs(self.dn_desc[i], lv.down_norm, G)
             self.up_stats[i], self.up_ss[i], self.up_mv[i] = self._stat_bufs(self.up_desc[i], lv.up_norm, G)
@@ -151,6 +166,12 @@ class UNetExecutor:
             self.g = [scratch] * D
         self.out = torch.empty(B, self.T_out, self.C_final, device=dev, dtype=torch.float32)
 
+    def layer_prec(self, side, level):
+        """Precision of the down ("d") or up ("u") convolution of a level."""
+        if self.prec == PG_PREC_F16X3 and f"{side}{level + 1}" in self.fast_layers:
+            return PG_PREC_F16X2
+        return self.prec
+
     def _stat_bufs(self, desc, has_norm, G):
         if not has_norm:
             return None, None, None
@@ -161,24 +182,27 @@ class UNetExecutor:
         return stats, ss, mv
 
     # ------------------------------------------------------------------------------ weights
-    def _pack_one(self, w, kind, slice_out=None):
+    def _pack_one(self, w, kind, slice_out=None, prec=None):
         """One weight -> (hi, lo, simt).  A weight whose memory is already the packed [k][C_out][C_in]
         order (the drop-in model's) is cast elementwise; any other layout goes through the
         transposing pack kernel."""
-        tc = self.prec != PG_PREC_FP32_SIMT
+        prec = self.prec if prec is None else prec
+        tc = prec != PG_PREC_FP32_SIMT
         if not tc:
             if slice_out is not None:
                 w = w[:, :slice_out]
             return ops.pack_weight(w.contiguous(), kind, want_tc=False, want_simt=True)
+        plane_dtype = torch.float16 if prec in _F16_PRECS else torch.bfloat16
+        want_lo = prec in (PG_PREC_BF16X3, PG_PREC_F16X3)          # the weight lo plane only feeds the third product
         pv = ops.packed_view(w, kind)
         if pv is None:
             if slice_out is not None:
                 w = w[:, :slice_out]
-            return ops.pack_weight(w.contiguous(), kind, want_tc=True, want_simt=False)
+            return ops.pack_weight(w.contiguous(), kind, want_tc=True, want_simt=False, plane_dtype=plane_dtype, want_lo=want_lo)
         if slice_out is not None:
             pv = pv[:, :slice_out].contiguous()
-        hi = torch.empty(pv.shape, device=pv.device, dtype=torch.bfloat16)
-        lo = torch.empty_like(hi) if self.prec == PG_PREC_BF16X3 else None
+        hi = torch.empty(pv.shape, device=pv.device, dtype=plane_dtype)
+        lo = torch.empty_like(hi) if want_lo else None
         ops.cast_split(pv, hi, lo)
         return hi, lo, None
 
@@ -187,9 +211,9 @@ class UNetExecutor:
         the first C_final output channels (phase-only inference)."""
         self.wd, self.wu = [], []
         for i, lv in enumerate(self.levels):
-            self.wd.append(self._pack_one(down_w[i], lv.down.kind))
+            self.wd.append(self._pack_one(down_w[i], lv.down.kind, None, self.layer_prec("d", i)))
             sl = self.C_final if (i == 0 and self.C_final != lv.up.C_out) else None
-            self.wu.append(self._pack_one(up_w[i], lv.up.kind, sl))
+            self.wu.append(self._pack_one(up_w[i], lv.up.kind, sl, self.layer_prec("u", i)))
 
     # ------------------------------------------------------------------------------ forward
     def _conv(self, desc, src, w, y, stats):
