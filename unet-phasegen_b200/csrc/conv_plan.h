@@ -9,6 +9,7 @@
 //       reads row m + (phi + p - k)/s of the (stride-1) input, l = m*s + phi.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/phasegen.h"
 #include "common.cuh"
@@ -107,7 +108,12 @@ static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
     // Several clips per tile when one clip's positions leave the 256-column accumulator mostly
     // empty: the weight tile is then shared by nb MMAs (one per clip).
     p->nb = 1;
-    if (p->n_ntiles == 1 && d->max_clips_per_tile != 1) {
+    // Fewer than three products per MAC (F16X2, BF16): the tensor pipe outruns the weight stream even for
+    // full-width tiles (measured: 72 % pipe-active at N = 176, profiles/r01_conv_tc_ncu_full_v2.csv), so two
+    // clips share every weight tile (2 x 176 accumulator columns, one TMEM stage); the three-product forms
+    // are pipe/power-bound there and keep the double-buffered accumulator.
+    const bool weight_bound = d->precision == PG_PREC_F16X2 || d->precision == PG_PREC_BF16;
+    if ((p->n_ntiles == 1 || weight_bound) && d->max_clips_per_tile != 1) {
         // Up to 512 accumulator columns (one TMEM stage) when the strips of that many clips still leave
         // room for the weight ring: the weight tile, the dominant L2->SM stream for short time axes, is
         // then shared by twice as many MMAs.  Otherwise up to 256 columns, double-buffered.
@@ -115,7 +121,7 @@ static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
         const int max_rows = (72 * 1024) / (planes * 128);          // rows of all clips' strips in one slot
         int nb = 512 / p->n_tile;
         if (nb * p->strip_rows > max_rows) nb = max_rows / p->strip_rows;
-        if (nb * p->n_tile <= 256 || p->n_tile > 128) {             // not worth giving up the second stage
+        if (nb * p->n_tile <= 256 || (p->n_tile > 128 && !weight_bound)) {   // not worth giving up the second stage
             nb = 256 / p->n_tile;
             if (nb * p->strip_rows > 256) nb = 256 / p->strip_rows;
         }
@@ -124,6 +130,10 @@ static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
         if (nb > d->B) nb = d->B;
         if (nb < 1) nb = 1;
         p->nb = nb;
+    }
+    if (const char* e = getenv("PG_TC_NB")) {                      // experiment hook: force the bundle size
+        int nb = atoi(e);
+        if (nb >= 1 && nb * p->n_tile <= 512 && nb <= d->B) p->nb = nb;
     }
     p->acc_stages = p->nb * p->n_tile <= 256 ? 2 : 1;
     p->clip_group = d->B;

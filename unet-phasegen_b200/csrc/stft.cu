@@ -6,282 +6,284 @@
 //   * expm1(mag) * exp(j*phase)                       demo.py:39, train.py:83
 //   * zero DC row + librosa.istft + peak normalise    utils.py:34-42
 //
-// Both kernels keep everything between the HBM read and the HBM write on chip:
-//   STFT : wave span -> smem (reflect padding resolved while loading) -> Hann window ->
-//          n_fft-point real FFT as an n_fft/2-point complex Stockham FFT (fft_core.cuh) ->
-//          Hermitian post-processing -> |X|, log1p, atan2 -> fp32 frame-major [B][T][C]
-//          (+ the bf16 hi/lo operand planes the first convolution consumes).
-//   ISTFT: (log-mag, phase) or (re, im) frame-major -> X -> half-length inverse FFT ->
-//          synthesis window -> GATHER overlap-add of the 4 frames that cover each output
-//          sample + window-sum-square normalisation -> fp32 wave.  No atomics on the output;
-//          the per-clip peak (for utils.py:42) is one atomicMax per CTA on a scalar.
+// Both kernels keep everything between the HBM read and the HBM write on chip (frame transforms:
+// stft_core.cuh, checked on the host by fft_selftest2.cpp):
+//   STFT : a frame is owned by n_fft/32 threads (one warp at n_fft 1024): windowed samples straight from
+//          global memory (float2, coalesced; the 75 % overlap between frames is served by L1/L2; reflect
+//          padding resolved on the edge frames only) -> n_fft/2-point complex Stockham FFT in a private
+//          shared buffer, passes separated by __syncwarp -> Hermitian post-processing (fused with the last
+//          radix-2 pass at n_fft 1024) -> log1p|X| (and atan2 only when the phase plane is requested)
+//          -> fp32 frame-major [B][T][C] + the 16-bit hi/lo operand planes the first convolution consumes.
+//          A CTA (8 warps) loops over 32+ frames so the twiddle/window tables are built once per CTA.
+//   ISTFT: a CTA walks a run of consecutive frames of one clip, 256/TG frames per iteration into a
+//          two-generation ring of windowed frames in shared memory; after each iteration it emits the
+//          output hop-blocks whose four covering frames are complete (GATHER overlap-add, window-sum-square
+//          normalisation, float4 stores).  Only 3 halo frames are recomputed per ~90-frame run (the first
+//          version recomputed 3 per 13).  No atomics on the output; the per-clip peak (utils.py:42) is one
+//          atomicMax per warp on a scalar.
 // hop must be n_fft/4 (true for every configuration of the reference and of BASELINE.json).
 #include "common.cuh"
-#include "fft_core.cuh"
+#include "stft_core.cuh"
 
 namespace pg {
 using namespace pgfft;
 
-template <int NC, int FR_> struct StftCfg {
-    static constexpr int TG = NC / 16;                      // threads per transform
-    static constexpr int FR = FR_;                          // frames per CTA
-    static constexpr int THREADS = TG * FR;
+constexpr int kStftThreads = 256;
+
+template <int NC> struct FrameCfg {
+    static constexpr int TG = NC / 16;                      // threads per frame
+    static constexpr int FC = kStftThreads / TG;            // frames in flight per CTA
     static constexpr int NFFT = 2 * NC;
     static constexpr int HOP = NFFT / 4;
-    static constexpr int PL = padded_len(NC);
-    static constexpr int SPAN = (FR - 1) * HOP + NFFT;      // wave samples a CTA touches
-    static constexpr size_t smem_stft() { return sizeof(float) * (3 * NFFT + SPAN + 2 * PL * FR); }
-    static constexpr size_t smem_istft() { return sizeof(float) * (3 * NFFT + 2 * PL * FR); }
+    static constexpr int PL = padded_len2(NC);              // float2 elements of one frame buffer
+    static constexpr size_t smem_stft() { return sizeof(float2) * (Radix<NC, false>::TOTAL + NC + (size_t)FC * PL); }
+    static constexpr int RING = FC + 3;                     // windowed frames kept on chip: this iteration's + 3 of the last
+    static constexpr size_t smem_istft() { return sizeof(float2) * (Radix<NC, true>::TOTAL + NC + (size_t)RING * PL) + sizeof(float) * HOP; }
 };
 
-// Forward transform whose first pass takes its inputs straight from the windowed wave span
-// (z[m] = x[2m] w[2m] + i x[2m+1] w[2m+1]) instead of a staged copy.
-template <int NC>
-__device__ __forceinline__ void fft_forward_from_span(float* sre, float* sim, const cpx* tw, const float* x, const float* win, int t) {
-    using P = Plan<NC>;
-    {
-        Pass<NC, P::R0, 1, false> p;
-        static_assert(P::R0 == 16, "first pass is one radix-16 butterfly per thread");
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const int m = t + r * (NC / 16);
-            const float2 xv = *reinterpret_cast<const float2*>(x + 2 * m);
-            const float2 wv = *reinterpret_cast<const float2*>(win + 2 * m);
-            p.v[r] = {xv.x * wv.x, xv.y * wv.y};
-        }
-        p.twiddle_butterfly(tw, t); p.store(sre, sim, t); __syncthreads();
+// the threads of one frame: lanes of a warp (TG <= 32) or two warps on a named barrier (TG = 64)
+template <int TG> struct FrameSync {
+    int slot;
+    __device__ __forceinline__ void operator()() const {
+        if (TG <= 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(TG) : "memory");
     }
-    {
-        Pass<NC, P::R1, P::R0, false> p;
-        p.load(sre, sim, t); __syncthreads();
-        p.twiddle_butterfly(tw, t); p.store(sre, sim, t); __syncthreads();
-    }
-    if (P::R2 > 1) {
-        Pass<NC, (P::R2 > 1 ? P::R2 : 2), P::R0 * P::R1, false> p;
-        p.load(sre, sim, t); __syncthreads();
-        p.twiddle_butterfly(tw, t); p.store(sre, sim, t); __syncthreads();
-    }
-}
+};
 
-// Inverse transform whose last pass applies the synthesis window while storing.
-template <int NC>
-__device__ __forceinline__ void fft_inverse_windowed(float* sre, float* sim, const cpx* tw, const float* win, int t) {
-    using P = Plan<NC>;
-    {
-        Pass<NC, P::R0, 1, true> p;
-        p.load(sre, sim, t); __syncthreads();
-        p.twiddle_butterfly(tw, t); p.store(sre, sim, t); __syncthreads();
-    }
-    {
-        Pass<NC, P::R1, P::R0, true> p;
-        p.load(sre, sim, t); __syncthreads();
-        p.twiddle_butterfly(tw, t);
-        if (P::R2 > 1) p.store(sre, sim, t); else p.store_windowed(sre, sim, t, win);
-        __syncthreads();
-    }
-    if (P::R2 > 1) {
-        Pass<NC, (P::R2 > 1 ? P::R2 : 2), P::R0 * P::R1, true> p;
-        p.load(sre, sim, t); __syncthreads();
-        p.twiddle_butterfly(tw, t); p.store_windowed(sre, sim, t, win); __syncthreads();
-    }
-}
-
-template <int NC, bool INV>
-__device__ __forceinline__ void fft_inplace(float* sre, float* sim, const cpx* tw, int t) {
-    using P = Plan<NC>;
-    {
-        Pass<NC, P::R0, 1, INV> p;
-        p.load(sre, sim, t); __syncthreads();
-        p.twiddle_butterfly(tw, t); p.store(sre, sim, t); __syncthreads();
-    }
-    {
-        Pass<NC, P::R1, P::R0, INV> p;
-        p.load(sre, sim, t); __syncthreads();
-        p.twiddle_butterfly(tw, t); p.store(sre, sim, t); __syncthreads();
-    }
-    if (P::R2 > 1) {
-        Pass<NC, (P::R2 > 1 ? P::R2 : 2), P::R0 * P::R1, INV> p;
-        p.load(sre, sim, t); __syncthreads();
-        p.twiddle_butterfly(tw, t); p.store(sre, sim, t); __syncthreads();
-    }
+__device__ __forceinline__ float fast_log1p_mag(float re, float im) {
+    const float m2 = fmaf(re, re, im * im);
+    const float mag = m2 > 0.f ? m2 * rsqrtf(m2) : 0.f;
+    return __logf(1.0f + mag);
 }
 
 // ------------------------------------------------------------------------------------ STFT
-template <int NC, int FR>
-__global__ void __launch_bounds__(StftCfg<NC, FR>::THREADS)
+// FAST = 0: every output selected at run time.  FAST = 1 / 2: the inference path (log-magnitude fp32 plane +
+// bf16 / fp16 hi,lo operand planes, no phase plane) with the selection compiled in.
+template <int NC, int FAST>
+__global__ void __launch_bounds__(kStftThreads)
 stft_kernel(const float* __restrict__ wave, int N, int T, const float2* __restrict__ tw_g, int mode,
             float* __restrict__ out_a, float* __restrict__ out_b,
             uint16_t* __restrict__ op_hi, uint16_t* __restrict__ op_lo,
-            long long op_batch_stride, int op_fmt) {
-    using Cfg = StftCfg<NC, FR>;
-    extern __shared__ float smem[];
-    cpx* tw = reinterpret_cast<cpx*>(smem);                 // [NFFT] exp(-2 pi i m / n_fft)
-    float* win = smem + 2 * Cfg::NFFT;                      // [NFFT] periodic Hann
-    float* span = win + Cfg::NFFT;                          // [SPAN]
-    float* bufs = span + Cfg::SPAN;                         // FR x (re[PL], im[PL])
+            long long op_batch_stride, int op_fmt, int frames_per_cta) {
+    using Cfg = FrameCfg<NC>;
+    using R = Radix<NC, false>;
+    extern __shared__ float2 smem2[];
+    cpx* tabs = reinterpret_cast<cpx*>(smem2);              // compact twiddle tables
+    cpx* win = tabs + R::TOTAL;                             // (w[2m], w[2m+1]) / 2, periodic Hann
+    cpx* bufs = win + NC;                                   // FC frame buffers
 
-    const int b = blockIdx.y;
-    const int t0 = blockIdx.x * Cfg::FR;                    // first frame of this CTA
     const int tid = threadIdx.x;
-    const float* w = wave + (size_t)b * N;
-
-    for (int i = tid; i < Cfg::NFFT; i += Cfg::THREADS) {
-        float2 v = __ldg(tw_g + i);
-        tw[i] = {v.x, v.y};
-        win[i] = 0.5f - 0.5f * v.x;                         // Hann(n) = 0.5 - 0.5 cos(2 pi n / n_fft)
-    }
-    // padded sample p <-> wave index p - n_fft/2, reflected at both ends (librosa center=True)
-    const int p0 = t0 * Cfg::HOP - NC;
-    for (int i = tid; i < Cfg::SPAN; i += Cfg::THREADS) {
-        int n = p0 + i;
-        if (n < 0) n = -n;
-        if (n >= N) n = 2 * (N - 1) - n;
-        span[i] = (n >= 0 && n < N) ? __ldg(w + n) : 0.f;
-    }
+    const cpx* twc = reinterpret_cast<const cpx*>(tw_g);
+    for (int e = tid; e < R::TOTAL; e += kStftThreads) tabs[e] = table_entry<NC, false>(twc, e);
+    for (int m = tid; m < NC; m += kStftThreads)            // Hann(n) = 0.5 - 0.5 cos(2 pi n / n_fft); the 1/2 of the
+        win[m] = {0.25f - 0.25f * tw_g[2 * m].x, 0.25f - 0.25f * tw_g[2 * m + 1].x};   // post-processing folded in
     __syncthreads();
 
-    const int f = tid / Cfg::TG, t = tid % Cfg::TG;
-    float* sre = bufs + f * 2 * Cfg::PL;
-    float* sim = sre + Cfg::PL;
-    fft_forward_from_span<NC>(sre, sim, tw, span + f * Cfg::HOP, win, t);
+    const int b = blockIdx.y;
+    const int slot = tid / Cfg::TG, t = tid % Cfg::TG;
+    cpx* s = bufs + slot * Cfg::PL;
+    const FrameSync<Cfg::TG> sync{slot};
+    const float* w = wave + (size_t)b * N;
+    const bool aligned = (N & 1) == 0 && (reinterpret_cast<uintptr_t>(wave) & 7) == 0;   // float2 loads
+    const int f_begin = blockIdx.x * frames_per_cta;
 
-    const int frame = t0 + f;
-    if (frame >= T) return;
-    const size_t row = (size_t)b * T + frame;
+    for (int f0 = f_begin; f0 < f_begin + frames_per_cta && f0 < T; f0 += Cfg::FC) {
+        const int frame = f0 + slot;
+        const bool live = frame < T;
+        // padded sample p <-> wave index p - n_fft/2, reflected at both ends (librosa center=True)
+        const int p0 = frame * Cfg::HOP - NC;
+        cpx v[16];
+        if (live && aligned && p0 >= 0 && p0 + Cfg::NFFT <= N) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        int k = 1 + t + i * Cfg::TG;                        // bins 1..NC (DC dropped)
-        int ka = k & (NC - 1), kb = (NC - k) & (NC - 1);
-        cpx zk = {sre[pad(ka)], sim[pad(ka)]};
-        cpx zm = {sre[pad(kb)], -sim[pad(kb)]};             // conj Z[NC-k]
-        cpx e = {0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y)};
-        cpx d = {0.5f * (zk.x - zm.x), 0.5f * (zk.y - zm.y)};
-        cpx o = {d.y, -d.x};                                // d / i
-        cpx x = cadd(e, cmul(tw[k], o));
-        if (k == NC) x.y = 0.f;
-        float a, ph;
-        if (mode == PG_STFT_LOGMAG) {
-            a = log1pf(sqrtf(x.x * x.x + x.y * x.y));
-            ph = atan2f(x.y, x.x);
+            for (int r = 0; r < 16; ++r) {
+                const int m = t + r * Cfg::TG;
+                const float2 xv = __ldg(reinterpret_cast<const float2*>(w + p0) + m);
+                const cpx wv = win[m];
+                v[r] = {xv.x * wv.x, xv.y * wv.y};
+            }
+        } else if (live) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int m = t + r * Cfg::TG;
+                int n0 = p0 + 2 * m, n1 = n0 + 1;
+                if (n0 < 0) n0 = -n0;
+                if (n0 >= N) n0 = 2 * (N - 1) - n0;
+                if (n1 < 0) n1 = -n1;
+                if (n1 >= N) n1 = 2 * (N - 1) - n1;
+                const float x0 = (n0 >= 0 && n0 < N) ? __ldg(w + n0) : 0.f;
+                const float x1 = (n1 >= 0 && n1 < N) ? __ldg(w + n1) : 0.f;
+                const cpx wv = win[m];
+                v[r] = {x0 * wv.x, x1 * wv.y};
+            }
         } else {
-            a = x.x; ph = x.y;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = {0.f, 0.f};
         }
-        size_t o_idx = row * NC + (k - 1);
-        if (out_a) out_a[o_idx] = a;
-        if (out_b) out_b[o_idx] = ph;
-        if (op_hi) {
-            uint16_t hi, lo;
-            split16(a, op_fmt, hi, lo);
-            size_t q = (size_t)b * op_batch_stride + (size_t)frame * NC + (k - 1);
-            op_hi[q] = hi;
-            if (op_lo) op_lo[q] = lo;
+        fwd_phase0<NC>(s, t, v);
+        sync();
+        fwd_phase1<NC>(s, t, tabs, sync);
+        sync();
+
+        const size_t row = ((size_t)b * T + frame) * NC;
+        const size_t orow = (size_t)b * op_batch_stride + (size_t)frame * NC;
+        auto emit = [&](int bin, cpx x) {
+            if (FAST) {
+                const float a = fast_log1p_mag(x.x, x.y);
+                uint16_t hi, lo;
+                split16(a, FAST == 2 ? PG_FMT_F16 : PG_FMT_BF16, hi, lo);
+                out_a[row + bin - 1] = a;
+                op_hi[orow + bin - 1] = hi;
+                op_lo[orow + bin - 1] = lo;
+                return;
+            }
+            if (bin == NC) x.y = 0.f;                       // the Nyquist bin of a real signal is real
+            float a, ph = 0.f;
+            if (mode == PG_STFT_LOGMAG) {
+                a = fast_log1p_mag(x.x, x.y);
+                if (out_b) ph = atan2f(x.y, x.x);
+            } else {
+                a = x.x; ph = x.y;
+            }
+            if (out_a) out_a[row + bin - 1] = a;
+            if (out_b) out_b[row + bin - 1] = ph;
+            if (op_hi) {
+                uint16_t hi, lo;
+                split16(a, op_fmt, hi, lo);
+                op_hi[orow + bin - 1] = hi;
+                if (op_lo) op_lo[orow + bin - 1] = lo;
+            }
+        };
+        if (NC == 512) {
+            if (live) fwd_fused_last_512(s, t, tabs, emit);
+        } else {
+            fwd_phase2_unfused<NC>(s, t, tabs, sync);
+            sync();
+            if (live) fwd_post_generic<NC>(s, t, tabs, emit);
         }
+        sync();                                             // the buffer is rewritten by the next frame
     }
 }
 
 // ----------------------------------------------------------------------------------- ISTFT
-template <int NC, int FR>
-__global__ void __launch_bounds__(StftCfg<NC, FR>::THREADS)
+__device__ __forceinline__ cpx spec_value(float a, float p, int mode) {
+    if (mode == PG_SPEC_CARTESIAN) return {a, p};
+    float mag = a;
+    if (mode == PG_SPEC_POLAR_LOG) {                        // expm1 (demo.py:39)
+        mag = __expf(a) - 1.0f;
+        if (fabsf(a) < 0.03f) mag = a * fmaf(a, fmaf(a, fmaf(a, 1.f / 24.f, 1.f / 6.f), 0.5f), 1.0f);
+    }
+    // the predicted phase is an unbounded real (model.py: no tanh): reduce to [-pi, pi] before the fast sin/cos
+    const float n = rintf(p * 0.15915494309189535f);
+    float r = fmaf(n, -6.2831854820251465f, p);
+    r = fmaf(n, 1.7484555e-7f, r);
+    return {mag * __cosf(r), mag * __sinf(r)};
+}
+
+// FAST: mode == PG_SPEC_POLAR_LOG with a phase plane (the inference path), selection compiled in.
+template <int NC, bool FAST>
+__global__ void __launch_bounds__(kStftThreads)
 istft_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int mode, int T,
              const float2* __restrict__ tw_g, float* __restrict__ wave,
-             unsigned* __restrict__ peak_bits, int* __restrict__ nonfinite) {
-    using Cfg = StftCfg<NC, FR>;
-    constexpr int H = Cfg::FR - 3;                          // output hop-blocks per CTA
-    extern __shared__ float smem[];
-    cpx* tw = reinterpret_cast<cpx*>(smem);
-    float* win = smem + 2 * Cfg::NFFT;
-    float* bufs = win + Cfg::NFFT;
+             unsigned* __restrict__ peak_bits, int* __restrict__ nonfinite, int blocks_per_cta) {
+    using Cfg = FrameCfg<NC>;
+    using R = Radix<NC, true>;
+    constexpr int FC = Cfg::FC, HOP = Cfg::HOP;
+    extern __shared__ float2 smem2[];
+    float* wss_full = reinterpret_cast<float*>(smem2);      // [HOP] sum of w^2 over the 4 covering frames (16-byte aligned)
+    cpx* tabs = reinterpret_cast<cpx*>(wss_full + HOP);
+    cpx* win = tabs + R::TOTAL;                             // synthesis Hann, (w[2m], w[2m+1])
+    cpx* ring = win + NC;                                   // RING = FC + 3 windowed frames, slot = (frame - F0) mod RING
+
+    const int tid = threadIdx.x;
+    const cpx* twc = reinterpret_cast<const cpx*>(tw_g);
+    for (int e = tid; e < R::TOTAL; e += kStftThreads) tabs[e] = table_entry<NC, true>(twc, e);
+    for (int m = tid; m < NC; m += kStftThreads) win[m] = {0.5f - 0.5f * tw_g[2 * m].x, 0.5f - 0.5f * tw_g[2 * m + 1].x};
+    for (int i = tid; i < HOP; i += kStftThreads) {
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float wn = 0.5f - 0.5f * tw_g[q * HOP + i].x; acc += wn * wn; }
+        wss_full[i] = acc;
+    }
+    __syncthreads();
 
     const int b = blockIdx.y;
-    const int j0 = blockIdx.x * H;                          // first output hop-block
-    const int tid = threadIdx.x;
-    const int n_out = (T - 1) * Cfg::HOP;
-
-    for (int i = tid; i < Cfg::NFFT; i += Cfg::THREADS) {
-        float2 v = __ldg(tw_g + i);
-        tw[i] = {v.x, v.y};
-        win[i] = 0.5f - 0.5f * v.x;
-    }
-
-    const int f = tid / Cfg::TG, t = tid % Cfg::TG;
-    float* sre = bufs + f * 2 * Cfg::PL;
-    float* sim = sre + Cfg::PL;
-    const int frame = j0 - 1 + f;                           // frames j0-1 .. j0+H+1
-    const bool live = frame >= 0 && frame < T;
-    const size_t row = ((size_t)b * T + (live ? frame : 0)) * NC;
-
-    // X[k], k = 1..NC from the inputs; X[0] = 0 (the zero DC row of utils.py:38-39)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        int k = 1 + t + i * Cfg::TG;
-        float xr = 0.f, xi = 0.f;
-        if (live) {
-            float a = __ldg(in_a + row + k - 1);
-            float p = in_b ? __ldg(in_b + row + k - 1) : 0.f;
-            if (mode == PG_SPEC_CARTESIAN) { xr = a; xi = p; }
-            else {
-                float mag = mode == PG_SPEC_POLAR_LOG ? expm1f(a) : a;
-                float s, c;
-                sincosf(p, &s, &c);
-                xr = mag * c; xi = mag * s;
-            }
-        }
-        if (k == NC) xi = 0.f;                              // irfft ignores Im of the Nyquist bin
-        sre[pad(k)] = xr;
-        sim[pad(k)] = xi;
-    }
-    if (t == 0) { sre[pad(0)] = 0.f; sim[pad(0)] = 0.f; }
-    __syncthreads();
-
-    // Z[k] = E[k] + i O[k],  E = (X[k] + conj X[NC-k]) / 2,  O = (X[k] - conj X[NC-k]) / 2 * W^-k.
-    // Thread handles the pair (k, NC-k) so the update is in place.  1/(2*NC) folded in here.
+    const int J0 = blockIdx.x * blocks_per_cta;             // output hop-blocks [J0, J1) of this CTA
+    const int J1 = min(J0 + blocks_per_cta, T - 1);
+    const int F0 = J0 - 1;                                  // first frame needed
+    const int n_iter = (J1 - J0 + 3 + FC - 1) / FC;
+    const int slot = tid / Cfg::TG, t = tid % Cfg::TG;
+    const FrameSync<Cfg::TG> sync{slot};
     const float scale = 0.5f / NC;
-    for (int k = t; k <= NC / 2; k += Cfg::TG) {
-        int km = NC - k;
-        cpx xk = {sre[pad(k)], sim[pad(k)]};
-        cpx xm = {sre[pad(km)], sim[pad(km)]};
-        cpx wk = tw[k];  wk.y = -wk.y;                      // W^-k
-        cpx wm = tw[km]; wm.y = -wm.y;
-        // for k
-        cpx e1 = {xk.x + xm.x, xk.y - xm.y};
-        cpx o1 = cmul({xk.x - xm.x, xk.y + xm.y}, wk);
-        cpx z1 = {(e1.x - o1.y) * scale, (e1.y + o1.x) * scale};
-        // for NC-k
-        cpx e2 = {xm.x + xk.x, xm.y - xk.y};
-        cpx o2 = cmul({xm.x - xk.x, xm.y + xk.y}, wm);
-        cpx z2 = {(e2.x - o2.y) * scale, (e2.y + o2.x) * scale};
-        sre[pad(k)] = z1.x; sim[pad(k)] = z1.y;
-        if (km < NC && km != k) { sre[pad(km)] = z2.x; sim[pad(km)] = z2.y; }
-    }
-    __syncthreads();
-    // x[2m] = Re z[m], x[2m+1] = Im z[m]; the last pass stores them already multiplied by the
-    // synthesis window.
-    fft_inverse_windowed<NC>(sre, sim, tw, win, t);
-
-    // gather overlap-add: output hop-block jb (trimmed coordinates) is covered by frames
-    // jb-1 .. jb+2; within frame jb-1+q the sample sits at offset (3-q)*hop + i.
-    float* wv = wave + (size_t)b * n_out;
+    float* wv = wave + (size_t)b * (size_t)(T - 1) * HOP;
     float pk = 0.f;
     bool bad = false;
-    for (int s = tid; s < H * Cfg::HOP; s += Cfg::THREADS) {
-        int jl = s / Cfg::HOP, i = s % Cfg::HOP;
-        int jb = j0 + jl;
-        if (jb >= T - 1) break;
-        float acc = 0.f, wss = 0.f;
+
+    // the 16 (a, b) input pairs of this thread's frame are fetched one iteration ahead of their use, so the
+    // global-load latency hides behind the previous frame's transform and overlap-add
+    float ra[16], rb[16];
+    auto is_live = [&](int frame) { return frame >= 0 && frame < T && frame <= J1 + 1; };
+    auto fetch = [&](int frame) {
+        if (!is_live(frame)) return;
+        const size_t row = ((size_t)b * T + frame) * NC;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            int fr = jb - 1 + q;
-            if (fr < 0 || fr >= T) continue;
-            int o = (3 - q) * Cfg::HOP + i;
-            const float* fb = bufs + (jl + q) * 2 * Cfg::PL + ((o & 1) ? Cfg::PL : 0);
-            acc += fb[pad(o >> 1)];
-            const float wn = win[o];
-            wss += wn * wn;
+        for (int j = 0; j < 16; ++j) {
+            const size_t idx = row + inv_bin<NC>(t, j) - 1;
+            ra[j] = __ldg(in_a + idx);
+            rb[j] = (FAST || in_b) ? __ldg(in_b + idx) : 0.f;
         }
-        float y = wss > 1.17549435e-38f ? acc / wss : acc;
-        wv[(size_t)jb * Cfg::HOP + i] = y;
-        if (!(fabsf(y) <= 3.402823466e+38f)) bad = true;
-        pk = fmaxf(pk, fabsf(y));
+    };
+    fetch(F0 + slot);
+
+    for (int it = 0; it < n_iter; ++it) {
+        const int F = F0 + it * FC;
+        const int frame = F + slot;
+        const bool live = is_live(frame);
+        cpx* s = ring + (size_t)((frame - F0) % Cfg::RING) * Cfg::PL;
+        if (live) {
+            cpx x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = spec_value(ra[j], rb[j], FAST ? (int)PG_SPEC_POLAR_LOG : mode);
+            if (NC == 512) inv_fused_first_512(s, t, tabs, scale, x);
+            else inv_pre_generic<NC>(s, t, tabs, scale, x);
+        }
+        if (it + 1 < n_iter) fetch(frame + FC);
+        sync();
+        inv_passes<NC>(s, t, tabs, win, sync);              // dead frames run on stale data; never read below
+        __syncthreads();
+
+        // output hop-block jb (trimmed coordinates) is covered by frames jb-1 .. jb+2; within frame
+        // jb-1+q its samples sit at offset (3-q)*hop + i
+        const int lo = max(J0, F - 2), hi = min(J1, F + FC - 2);
+        for (int u = tid; u < (hi - lo) * (HOP / 4); u += kStftThreads) {
+            const int jb = lo + u / (HOP / 4), i = (u % (HOP / 4)) * 4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), wss;
+            const bool interior = jb >= 1 && jb + 2 < T;
+            if (interior) wss = *reinterpret_cast<const float4*>(wss_full + i);
+            else wss = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int fr = jb - 1 + q;
+                if (fr < 0 || fr >= T) continue;
+                const cpx* fb = ring + (size_t)((fr - F0) % Cfg::RING) * Cfg::PL;
+                const int m = ((3 - q) * HOP + i) >> 1;
+                const cpx z0 = fb[pad2(m)], z1 = fb[pad2(m + 1)];
+                acc.x += z0.x; acc.y += z0.y; acc.z += z1.x; acc.w += z1.y;
+                if (!interior) {
+                    const cpx w0 = win[m], w1 = win[m + 1];
+                    wss.x += w0.x * w0.x; wss.y += w0.y * w0.y; wss.z += w1.x * w1.x; wss.w += w1.y * w1.y;
+                }
+            }
+            float4 y;
+            y.x = wss.x > 1.17549435e-38f ? acc.x / wss.x : acc.x;
+            y.y = wss.y > 1.17549435e-38f ? acc.y / wss.y : acc.y;
+            y.z = wss.z > 1.17549435e-38f ? acc.z / wss.z : acc.z;
+            y.w = wss.w > 1.17549435e-38f ? acc.w / wss.w : acc.w;
+            *reinterpret_cast<float4*>(wv + (size_t)jb * HOP + i) = y;
+            const float mx = fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w)));
+            if (!(mx <= 3.402823466e+38f) || y.x != y.x || y.y != y.y || y.z != y.z || y.w != y.w) bad = true;
+            pk = fmaxf(pk, mx);
+        }
+        __syncthreads();                                    // the next iteration overwrites the oldest FC frames
     }
     if (peak_bits) {
 #pragma unroll
@@ -297,41 +299,55 @@ __global__ void peak_normalize_kernel(float* __restrict__ wave, const unsigned* 
     if (!(pk >= 1.17549435e-38f)) return;                   // librosa.util.normalize: tiny -> unchanged
     float inv = 1.0f / pk;
     float* w = wave + (size_t)b * n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) w[i] = w[i] * inv;
+    if ((n & 3) == 0) {
+        float4* w4 = reinterpret_cast<float4*>(w);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += gridDim.x * blockDim.x) {
+            float4 v = w4[i];
+            v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+            w4[i] = v;
+        }
+    } else {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) w[i] = w[i] * inv;
+    }
 }
-
-// frames per CTA: 256 threads for the forward transform; the inverse recomputes a 3-frame halo
-// per CTA, so it takes more frames per CTA to amortise it.
-template <int NC> struct FramesPerCta {
-    static constexpr int STFT = NC >= 1024 ? 8 : 256 / (NC / 16);
-    static constexpr int ISTFT = NC >= 1024 ? 8 : 16;
-};
 
 template <int NC>
 static int launch_stft(const float* wave, int B, int N, int T, const float* tw, int mode, float* a, float* bq,
                        uint16_t* hi, uint16_t* lo, long long bs, int fmt, cudaStream_t st) {
-    constexpr int FR = FramesPerCta<NC>::STFT;
-    using Cfg = StftCfg<NC, FR>;
-    auto k = stft_kernel<NC, FR>;
-    size_t sm = Cfg::smem_stft();
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    dim3 grid((T + Cfg::FR - 1) / Cfg::FR, B);
-    k<<<grid, Cfg::THREADS, sm, st>>>(wave, N, T, reinterpret_cast<const float2*>(tw), mode, a, bq, hi, lo, bs, fmt);
+    using Cfg = FrameCfg<NC>;
+    const bool fast = mode == PG_STFT_LOGMAG && a && !bq && hi && lo;
+    auto k = !fast ? stft_kernel<NC, 0> : fmt == PG_FMT_F16 ? stft_kernel<NC, 2> : stft_kernel<NC, 1>;
+    const size_t sm = Cfg::smem_stft();
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(stft_kernel<NC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaFuncSetAttribute(stft_kernel<NC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaFuncSetAttribute(stft_kernel<NC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        configured = true;
+    }
+    const int frames_per_cta = Cfg::FC * 4;                 // tables are built once per 4 passes over the frame slots
+    dim3 grid((T + frames_per_cta - 1) / frames_per_cta, B);
+    k<<<grid, kStftThreads, sm, st>>>(wave, N, T, reinterpret_cast<const float2*>(tw), mode, a, bq, hi, lo, bs, fmt, frames_per_cta);
     return check_launch("stft_kernel");
 }
 
 template <int NC>
 static int launch_istft(const float* a, const float* bq, int mode, int B, int T, const float* tw, float* wave,
                         float* peak, int* nonfinite, cudaStream_t st) {
-    constexpr int FR = FramesPerCta<NC>::ISTFT;
-    using Cfg = StftCfg<NC, FR>;
-    constexpr int H = Cfg::FR - 3;
-    auto k = istft_kernel<NC, FR>;
-    size_t sm = Cfg::smem_istft();
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    dim3 grid((T - 1 + H - 1) / H, B);
-    k<<<grid, Cfg::THREADS, sm, st>>>(a, bq, mode, T, reinterpret_cast<const float2*>(tw), wave,
-                                     reinterpret_cast<unsigned*>(peak), nonfinite);
+    using Cfg = FrameCfg<NC>;
+    auto k = (mode == PG_SPEC_POLAR_LOG && bq) ? istft_kernel<NC, true> : istft_kernel<NC, false>;
+    const size_t sm = Cfg::smem_istft();
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(istft_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaFuncSetAttribute(istft_kernel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        configured = true;
+    }
+    // a run of 11 iterations: 11*FC - 3 output blocks per CTA, 3 halo frames recomputed per run
+    const int blocks_per_cta = 11 * Cfg::FC - 3;
+    dim3 grid((T - 1 + blocks_per_cta - 1) / blocks_per_cta, B);
+    k<<<grid, kStftThreads, sm, st>>>(a, bq, mode, T, reinterpret_cast<const float2*>(tw), wave,
+                                     reinterpret_cast<unsigned*>(peak), nonfinite, blocks_per_cta);
     return check_launch("istft_kernel");
 }
 
