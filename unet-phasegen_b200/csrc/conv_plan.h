@@ -31,6 +31,10 @@ struct ConvPlan {
     int acc_stages;             // TMEM accumulator stages: 2 (nb*n_tile <= 256, epilogue overlaps MMA) or 1 (up to 512 columns)
     int pair;                   // tensor-core path: tiles are 256 channels wide, owned by a CTA pair (cta_group::2); strip_rows
                                 // is then the half strip (n_tile/2 + largest shift) each CTA of the pair loads
+    int mgroups;                // merged tiles: MMAs per weight tile (1 or 2); nb = mgroups * clips per MMA
+    int merged;                 // tensor-core path, short time axes: the nb/mgroups clips of a group are ONE MMA of N = (nb/mgroups)*strip_rows
+                                // (accumulator column pitch strip_rows per clip, the strip_rows - n_tile columns between clips
+                                // are junk); strip_rows is the full strip, a CTA pair splits the tile by clips
     int clip_group;             // tensor-core tile order: clips per L2-resident group (set by the launcher)
     int out_rows, out_ld;
     int n_groups[2], n_taps[2];
@@ -135,7 +139,44 @@ static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
         int nb = atoi(e);
         if (nb >= 1 && nb * p->n_tile <= 512 && nb <= d->B) p->nb = nb;
     }
-    p->acc_stages = p->nb * p->n_tile <= 256 ? 2 : 1;
+    // Merged clips.  With one MMA per clip a short time axis means tiny MMAs (N = 16..96) whose fixed operand-fetch
+    // cost dominates (measured ~32 + N/2 cycles per MMA) and few tiles.  Laying the clips' strips end to end
+    // makes them one N = nb*strip_rows operand: a tap shifted by s rows reads rows [s, s + N), so clip c's
+    // outputs land in columns [c*strip_rows, c*strip_rows + n_tile) and the columns in between (fed by rows that
+    // straddle two clips) are never read back.  nb minimises waves x (32 + N/2) over the persistent grid.
+    p->merged = 0; p->mgroups = 1;
+    {
+        const int strip_full = (p->n_tile + max_shift + 7) / 8 * 8;
+        const int step = p->pair ? 2 : 1;
+        int nb_max = 256 / strip_full;
+        if (nb_max > d->B) nb_max = d->B;
+        if (d->max_clips_per_tile > 1 && nb_max > d->max_clips_per_tile) nb_max = d->max_clips_per_tile;
+        nb_max -= nb_max % step;
+        const char* off = getenv("PG_TC_MERGED");
+        if (p->n_ntiles == 1 && nb_max >= 2 && d->max_clips_per_tile != 1 && !(off && atoi(off) == 0)) {
+            const int units = (d->tc_max_ctas > 0 ? d->tc_max_ctas : 148) / (p->pair ? 2 : 1);
+            const int slabs = (p->pair ? p->n_cotiles / 2 : p->n_cotiles) * p->OS;
+            long best = -1; int best_nb = step;
+            for (int nb = step; nb <= nb_max; nb += step) {
+                const long tiles = (long)slabs * ((d->B + nb - 1) / nb);
+                const long cost = ((tiles + units - 1) / units) * (64 + (long)nb * strip_full);
+                if (best < 0 || cost <= best) { best = cost; best_nb = nb; }
+            }
+            p->merged = 1; p->nb = best_nb; p->strip_rows = strip_full;
+            // Two MMAs (2 x up to 256 accumulator columns, one TMEM stage) per weight tile while that still leaves
+            // a tile for every CTA (pair): the weight stream from L2 -- the bound of these layers, whose
+            // weights are read once per tile -- halves.
+            const long tiles2 = (long)slabs * ((d->B + 2 * best_nb - 1) / (2 * best_nb));
+            const char* g2 = getenv("PG_TC_MGROUPS");
+            const int planes_b = (d->precision == PG_PREC_BF16X3 || d->precision == PG_PREC_F16X3 || d->precision == PG_PREC_F16X2) ? 2 : 1;
+            const long slot_bytes = (long)planes_b * (2 * best_nb / (p->pair ? 2 : 1)) * strip_full * 128;   // per CTA, one strip slot
+            if (2 * best_nb <= d->B && 2 * best_nb * strip_full <= 512 && tiles2 >= units && 2 * slot_bytes <= 120 * 1024 &&
+                !(g2 && atoi(g2) == 1)) {
+                p->mgroups = 2; p->nb = 2 * best_nb;
+            }
+        }
+    }
+    p->acc_stages = (p->merged ? p->nb * p->strip_rows : p->nb * p->n_tile) <= 256 ? 2 : 1;
     p->clip_group = d->B;
     return PG_OK;
 }

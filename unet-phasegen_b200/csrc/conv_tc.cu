@@ -129,18 +129,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
     const int rank = PAIR ? (int)cluster_ctarank() : 0;           // 0 = leader (issues the MMAs)
     const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const int half_n = pl.n_tile >> 1;                            // PAIR: positions each CTA supplies per clip
+    const int half_n = pl.n_tile >> 1;                            // PAIR, not merged: positions each CTA supplies per clip
+    const int nb_grp = pl.nb / pl.mgroups;                        // clips per MMA (merged) / per tile (mgroups = 1)
+    const int nb_cta = (PAIR && pl.merged) ? nb_grp >> 1 : nb_grp;   // clips of one group whose strips this CTA loads
+    const int col_pitch = pl.merged ? pl.strip_rows : pl.n_tile;  // accumulator columns per clip
 
     if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0) {
             uint32_t a_it = 0, b_it = 0;
+            const uint32_t grp_bytes = (uint32_t)nb_cta * pl.strip_rows * 128u;   // one merged group's strips in this CTA
             const uint32_t a_bytes = a_planes * kATileBytes;
             const uint32_t b_bytes = b_planes * (uint32_t)bPlane;
             for (int tile = tile0; tile < n_tiles; tile += tile_step) {
                 TileCoord tc = decode_tile(pl, tile);
                 if (PAIR) tc.co_tile = tc.co_tile * 2 + rank;
-                const int m0 = tc.nt * pl.n_tile + (PAIR ? rank * half_n : 0);
+                const int m0 = tc.nt * pl.n_tile + ((PAIR && !pl.merged) ? rank * half_n : 0);
+                const int clip0 = tc.b0 + ((PAIR && pl.merged) ? rank * nb_cta : 0);   // + g * nb_grp per merged group
                 const int ng = pl.n_groups[tc.phase];
                 for (int ch = 0; ch < pl.n_chunks; ++ch) {
                     for (int g = 0; g < ng; ++g) {
@@ -149,14 +154,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                             const int s = b_it & 1; const uint32_t ph = (b_it >> 1) & 1;
                             mbar_wait(emptyB + s, ph ^ 1);
                             uint8_t* dst = b_base + (size_t)s * b_planes * bPlane;
-                            if (PAIR) {
-                                if (rank == 0) mbar_expect_tx(fullB + s, 2 * b_bytes);     // both CTAs' halves
-                                tma_load_4d_pair(dst, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
-                                if (x_lo) tma_load_4d_pair(dst + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
-                            } else {
-                                mbar_expect_tx(fullB + s, b_bytes);
-                                tma_load_4d(dst, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
-                                if (x_lo) tma_load_4d(dst + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, tc.b0);
+                            if (PAIR) { if (rank == 0) mbar_expect_tx(fullB + s, 2 * b_bytes); }   // both CTAs' halves
+                            else mbar_expect_tx(fullB + s, b_bytes);
+                            for (int mg = 0; mg < pl.mgroups; ++mg) {      // one box per merged group (its clips are contiguous)
+                                uint8_t* dg = dst + (size_t)mg * grp_bytes;
+                                const int cg = clip0 + mg * nb_grp;
+                                if (PAIR) {
+                                    tma_load_4d_pair(dg, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
+                                    if (x_lo) tma_load_4d_pair(dg + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
+                                } else {
+                                    tma_load_4d(dg, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
+                                    if (x_lo) tma_load_4d(dg + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
+                                }
                             }
                             ++b_it;
                         }
@@ -193,7 +202,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
         if (rank == 0) {
             uint32_t a_it = 0, b_it = 0, t_it = 0;
             // operand format field: 1 = bf16, 0 = fp16 (bits [7,10) for A, [10,13) for B)
-            const uint32_t idesc = (make_idesc_bf16(pl.n_tile, PAIR ? 256 : 128) & ~(prm.f16 ? ((7u << 7) | (7u << 10)) : 0u)) |
+            const int n_mma = pl.merged ? nb_grp * pl.strip_rows : pl.n_tile;
+            const int n_loop = pl.merged ? pl.mgroups : pl.nb;    // merged: one MMA covers every clip of a group
+            const uint32_t idesc = (make_idesc_bf16(n_mma, PAIR ? 256 : 128) & ~(prm.f16 ? ((7u << 7) | (7u << 10)) : 0u)) |
                                    (prm.a_mn ? (1u << 15) : 0u);
             const bool a_mn = prm.a_mn != 0;
             auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc_flag) {
@@ -212,7 +223,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 const int ng = pl.n_groups[tc.phase];
                 uint32_t accumulate = 0, accumulate_rest = 0;
-                const uint32_t clip_bytes = (uint32_t)pl.strip_rows * 128u;
+                const uint32_t clip_bytes = pl.merged ? (uint32_t)nb_cta * pl.strip_rows * 128u : (uint32_t)pl.strip_rows * 128u;
+                const uint32_t col_step = pl.merged ? (uint32_t)n_mma : (uint32_t)pl.n_tile;
                 for (int ch = 0; ch < pl.n_chunks; ++ch) {
                     for (int g = 0; g < ng; ++g) {
                         const ConvGroup grp = pl.groups[tc.phase][g];
@@ -229,9 +241,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                             const uint32_t a_hi = smem_u32(a_base + (size_t)as * a_planes * kATileBytes);
                             const uint32_t a_lo = a_hi + kATileBytes;
                             const uint32_t sh = (uint32_t)tp.shift * 128u;
-                            for (int c = 0; c < pl.nb; ++c) {      // one MMA group per clip of the bundle
+                            for (int c = 0; c < n_loop; ++c) {     // one MMA group per clip of the bundle
                                 const uint32_t boff = (uint32_t)c * clip_bytes + sh;
-                                const uint32_t dcol = d_tmem + c * pl.n_tile;
+                                const uint32_t dcol = d_tmem + c * col_step;
                                 const uint32_t acc_c = c == 0 ? accumulate : accumulate_rest;
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk) {   // 4 x (K = 16) per 64-channel chunk
@@ -281,7 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
             for (int c = 0; c < pl.nb; ++c) {
                 const int b = tc.b0 + c;
                 if (b >= pl.B) break;
-                const uint32_t taddr = tmem_base + acc * 256 + c * pl.n_tile + ((uint32_t)(q * 32) << 16);
+                const uint32_t taddr = tmem_base + acc * 256 + c * col_pitch + ((uint32_t)(q * 32) << 16);
                 // pass 1: mean over the valid columns
                 float sum = 0.f;
                 for (int c0 = 0; c0 < n_valid; c0 += 16) {
@@ -386,9 +398,12 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     prm.f16 = (d->precision == PG_PREC_F16X3 || d->precision == PG_PREC_F16X2) ? 1 : 0;
     prm.base_offset_mode = d->tc_base_offset_mode;
     prm.a_mn = d->weights_mn_major ? 1 : 0;
-    prm.b_slot_bytes = pl.nb * pl.strip_rows * 128;
+    const int nb_grp = pl.nb / pl.mgroups;
+    const int nb_cta = (pl.pair && pl.merged) ? nb_grp / 2 : nb_grp;
+    prm.b_slot_bytes = pl.mgroups * nb_cta * pl.strip_rows * 128;
     const int a_planes = n_terms == 3 ? 2 : 1, b_planes = n_terms >= 2 ? 2 : 1;
-    const int fixed = 2 * b_planes * prm.b_slot_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    // merged tiles read up to 15 rows past the last strip (junk columns only): 2 KB of slack keeps that inside the allocation
+    const int fixed = 2 * b_planes * prm.b_slot_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + (pl.merged ? 2048 : 0);
     int nA = (g_max_smem - fixed) / (a_planes * kATileBytes);
     if (nA > kMaxASlots) nA = kMaxASlots;
     PG_REQUIRE(nA >= 2, "pg_conv_tc: strip of %d rows leaves no room for the weight ring", pl.strip_rows);
@@ -411,7 +426,7 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
         const int IS = pl.IS;
         uint64_t dims[4] = {(uint64_t)d->C_in, (uint64_t)IS, (uint64_t)((d->L_in + IS - 1) / IS), (uint64_t)d->B};
         uint64_t str[3] = {(uint64_t)d->in_ld * 2, (uint64_t)d->in_ld * 2 * IS, (uint64_t)d->in_rows * d->in_ld * 2};
-        uint32_t box[4] = {64, 1, (uint32_t)pl.strip_rows, (uint32_t)pl.nb};
+        uint32_t box[4] = {64, 1, (uint32_t)pl.strip_rows, (uint32_t)nb_cta};
         PG_REQUIRE(d->in_rows >= ((d->L_in + IS - 1) / IS) * IS, "pg_conv_tc: in_rows %d too small for L_in %d at stride %d", d->in_rows, d->L_in, IS);
         if ((rc = encode_bf16_map(&mx_hi, x_hi, 4, dims, str, box, "x_hi")) != PG_OK) return rc;
         if ((rc = encode_bf16_map(&mx_lo, n_terms >= 2 ? x_lo : x_hi, 4, dims, str, box, "x_lo")) != PG_OK) return rc;
