@@ -40,11 +40,17 @@ int pg_check_device(int* sm_count, int* cc_major, int* cc_minor);
  * 16-bit hi/lo planes (op_fmt: PG_FMT_BF16 or PG_FMT_F16) [B][..][n_fft/2] with op_batch_stride
  * elements between clips -- the operand of the first convolution.  twiddle: float2[n_fft] = exp(-2*pi*i*m/n_fft).
  * n_fft in {256,512,1024,2048}, hop = n_fft/4. */
-enum { PG_STFT_LOGMAG = 0, PG_STFT_REIM = 1 };
+enum { PG_STFT_LOGMAG = 0, PG_STFT_REIM = 1, PG_STFT_PROJECT = 2 /* pg_stft_project only */ };
 int pg_stft_num_frames(int n_samples, int hop);
 int pg_stft(const float* wave, int B, int N, int n_fft, int hop, const float* twiddle, int mode,
             float* out_a, float* out_b, uint16_t* op_hi, uint16_t* op_lo, int64_t op_batch_stride,
             int op_fmt, pg_stream stream);
+
+/* One Griffin-Lim projection (utils.py:119-124: recon_spec = stft(recon_aud) without the DC row; new_spec =
+ * spec * exp(1j * angle(recon_spec))): out = mag * X / |X| as (re, im) planes, frame-major [B][T][n_fft/2],
+ * ready for pg_istft(PG_SPEC_CARTESIAN).  mag: the target magnitude [B][T][n_fft/2]. */
+int pg_stft_project(const float* wave, int B, int N, int n_fft, int hop, const float* twiddle,
+                    const float* mag, float* out_re, float* out_im, pg_stream stream);
 
 /* ---------------------------------------------------------------- ISTFT back end
  * Replaces utils.generate_audio (utils.py:11-44): zero DC row (:38-39), librosa.istft (:40:

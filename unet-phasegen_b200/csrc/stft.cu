@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kStftThreads)
 stft_kernel(const float* __restrict__ wave, int N, int T, const float2* __restrict__ tw_g, int mode,
             float* __restrict__ out_a, float* __restrict__ out_b,
             uint16_t* __restrict__ op_hi, uint16_t* __restrict__ op_lo,
-            long long op_batch_stride, int op_fmt, int frames_per_cta) {
+            long long op_batch_stride, int op_fmt, int frames_per_cta, const float* __restrict__ proj_mag) {
     using Cfg = FrameCfg<NC>;
     using R = Radix<NC, false>;
     extern __shared__ float2 smem2[];
@@ -138,7 +138,15 @@ stft_kernel(const float* __restrict__ wave, int N, int T, const float2* __restri
             }
             if (bin == NC) x.y = 0.f;                       // the Nyquist bin of a real signal is real
             float a, ph = 0.f;
-            if (mode == PG_STFT_LOGMAG) {
+            if (mode == PG_STFT_PROJECT) {
+                // Griffin-Lim projection (utils.py:119-124): keep the phase of X, impose the magnitude proj_mag;
+                // X / |X| directly instead of exp(j * angle(X)); angle(0) = 0 -> unit vector (1, 0)
+                const float m2 = fmaf(x.x, x.x, x.y * x.y);
+                const float inv = m2 > 0.f ? rsqrtf(m2) : 0.f;
+                const float g = __ldg(proj_mag + row + bin - 1);
+                a = m2 > 0.f ? g * x.x * inv : g;
+                ph = g * x.y * inv;
+            } else if (mode == PG_STFT_LOGMAG) {
                 a = fast_log1p_mag(x.x, x.y);
                 if (out_b) ph = atan2f(x.y, x.x);
             } else {
@@ -313,7 +321,7 @@ __global__ void peak_normalize_kernel(float* __restrict__ wave, const unsigned* 
 
 template <int NC>
 static int launch_stft(const float* wave, int B, int N, int T, const float* tw, int mode, float* a, float* bq,
-                       uint16_t* hi, uint16_t* lo, long long bs, int fmt, cudaStream_t st) {
+                       uint16_t* hi, uint16_t* lo, long long bs, int fmt, cudaStream_t st, const float* proj_mag = nullptr) {
     using Cfg = FrameCfg<NC>;
     const bool fast = mode == PG_STFT_LOGMAG && a && !bq && hi && lo;
     auto k = !fast ? stft_kernel<NC, 0> : fmt == PG_FMT_F16 ? stft_kernel<NC, 2> : stft_kernel<NC, 1>;
@@ -327,7 +335,7 @@ static int launch_stft(const float* wave, int B, int N, int T, const float* tw, 
     }
     const int frames_per_cta = Cfg::FC * 4;                 // tables are built once per 4 passes over the frame slots
     dim3 grid((T + frames_per_cta - 1) / frames_per_cta, B);
-    k<<<grid, kStftThreads, sm, st>>>(wave, N, T, reinterpret_cast<const float2*>(tw), mode, a, bq, hi, lo, bs, fmt, frames_per_cta);
+    k<<<grid, kStftThreads, sm, st>>>(wave, N, T, reinterpret_cast<const float2*>(tw), mode, a, bq, hi, lo, bs, fmt, frames_per_cta, proj_mag);
     return check_launch("stft_kernel");
 }
 
@@ -372,6 +380,24 @@ extern "C" int pg_stft(const float* wave, int B, int N, int n_fft, int hop, cons
         case 2048: return pg::launch_stft<1024>(wave, B, N, T, twiddle, mode, out_a, out_b, op_hi, op_lo, op_batch_stride, op_fmt, st);
     }
     pg::set_error("pg_stft: n_fft must be 256, 512, 1024 or 2048 (got %d)", n_fft);
+    return PG_ERR_UNSUPPORTED;
+}
+
+extern "C" int pg_stft_project(const float* wave, int B, int N, int n_fft, int hop, const float* twiddle, const float* mag,
+                               float* out_re, float* out_im, pg_stream stream) {
+    PG_REQUIRE(wave && twiddle && mag && out_re && out_im && B > 0 && N > 0, "pg_stft_project: null pointer or empty batch");
+    PG_REQUIRE(hop * 4 == n_fft, "pg_stft_project: hop must be n_fft/4 (got n_fft=%d hop=%d)", n_fft, hop);
+    PG_REQUIRE(N > n_fft / 2, "pg_stft_project: reflect padding needs more than n_fft/2 samples (N=%d)", N);
+    PG_REQUIRE(B <= 65535, "pg_stft_project: batch too large for one launch");
+    const int T = 1 + N / hop;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (n_fft) {
+        case 256:  return pg::launch_stft<128>(wave, B, N, T, twiddle, PG_STFT_PROJECT, out_re, out_im, nullptr, nullptr, 0, 0, st, mag);
+        case 512:  return pg::launch_stft<256>(wave, B, N, T, twiddle, PG_STFT_PROJECT, out_re, out_im, nullptr, nullptr, 0, 0, st, mag);
+        case 1024: return pg::launch_stft<512>(wave, B, N, T, twiddle, PG_STFT_PROJECT, out_re, out_im, nullptr, nullptr, 0, 0, st, mag);
+        case 2048: return pg::launch_stft<1024>(wave, B, N, T, twiddle, PG_STFT_PROJECT, out_re, out_im, nullptr, nullptr, 0, 0, st, mag);
+    }
+    pg::set_error("pg_stft_project: n_fft must be 256, 512, 1024 or 2048 (got %d)", n_fft);
     return PG_ERR_UNSUPPORTED;
 }
 

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "pg_check_device": (_I, [C.POINTER(_I)] * 3),
     "pg_stft_num_frames": (_I, [_I, _I]),
     "pg_stft": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _L, _I, _P]),
+    "pg_stft_project": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "pg_istft": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "pg_peak_normalize": (_I, [_P, _P, _I, _I, _P]),
     "pg_pack_weight": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),

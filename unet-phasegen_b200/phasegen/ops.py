@@ -78,7 +78,23 @@ def stft(wave, n_fft, hop, mode=PG_STFT_LOGMAG, want_second=True, operand=None):
     return a, b
 
 
-def istft(a, b, mode, n_fft, hop, normalize=True, check_finite=True):
+def stft_project(wave, mag, n_fft, hop, out=None):
+    """One Griffin-Lim projection: STFT of wave [B,N], phase kept, magnitude replaced by mag [B,T,C]
+    -> (re, im) fp32 [B,T,C] for istft(..., PG_SPEC_CARTESIAN).  `out` = (re, im) buffers to reuse."""
+    check_stft_geometry(n_fft, hop)
+    wave = _need_cuda(wave, "wave")
+    mag = _need_cuda(mag, "mag")
+    B, N = wave.shape
+    T = 1 + N // hop
+    if tuple(mag.shape) != (B, T, n_fft // 2):
+        raise RuntimeError(f"phasegen.stft_project: mag must be [{B}, {T}, {n_fft // 2}], got {tuple(mag.shape)}")
+    re, im = out if out is not None else (torch.empty_like(mag), torch.empty_like(mag))
+    _lib.call("pg_stft_project", _ptr(wave), B, N, n_fft, hop, _ptr(twiddle(n_fft, wave.device)), _ptr(mag),
+              _ptr(re), _ptr(im), _stream())
+    return re, im
+
+
+def istft(a, b, mode, n_fft, hop, normalize=True, check_finite=True, out=None):
     """(a, b) fp32 [B,T,n_fft/2] frame-major -> wave [B,(T-1)*hop]; optional peak normalisation
     (utils.py:42) and finiteness check (utils.py:41; costs one device->host sync)."""
     check_stft_geometry(n_fft, hop)
@@ -88,7 +104,9 @@ def istft(a, b, mode, n_fft, hop, normalize=True, check_finite=True):
     if Cb != n_fft // 2 or (b is not None and b.shape != a.shape):
         raise RuntimeError("phasegen.istft: inputs must be [B, T, n_fft/2] and of equal shape")
     n = (T - 1) * hop
-    wave = torch.empty(B, n, device=a.device, dtype=torch.float32)
+    if out is not None and (tuple(out.shape) != (B, n) or out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous()):
+        raise RuntimeError(f"phasegen.istft: `out` must be a contiguous CUDA float32 [{B}, {n}] tensor")
+    wave = out if out is not None else torch.empty(B, n, device=a.device, dtype=torch.float32)
     peak = torch.empty(B, device=a.device, dtype=torch.float32)
     bad = torch.empty(B, device=a.device, dtype=torch.int32)
     _lib.call("pg_istft", _ptr(a), _ptr(b), mode, B, T, n_fft, hop, _ptr(twiddle(n_fft, a.device)),

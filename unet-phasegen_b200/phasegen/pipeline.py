@@ -21,7 +21,7 @@ class PhaseGenPipeline:
     def frames(self, n_samples):
         return 1 + n_samples // self.hop
 
-    def __call__(self, wave, check_finite=False, return_intermediates=False):
+    def __call__(self, wave, check_finite=False, return_intermediates=False, wave_out=None):
         """wave float32 [B, N] on the GPU, N = (T-1)*hop with T % 8 == 0 -> float32 [B, N]."""
         if not wave.is_cuda:
             raise RuntimeError("PhaseGenPipeline needs CUDA tensors: there is no CPU fallback")
@@ -42,7 +42,7 @@ class PhaseGenPipeline:
         C = self.n_fft // 2
         phase = out if out.shape[2] == C else out[:, :, :C].contiguous()
         audio, peak = ops.istft(logmag, phase, PG_SPEC_POLAR_LOG, self.n_fft, self.hop,
-                                normalize=self.normalize, check_finite=check_finite)
+                                normalize=self.normalize, check_finite=check_finite, out=wave_out)
         if return_intermediates:
             return audio, logmag, phase
         return audio
@@ -50,33 +50,48 @@ class PhaseGenPipeline:
     def run_host(self, host_in, host_out, chunks=4):
         """End-to-end call on HOST buffers (pinned float32 [B, N] in and out): the batch is cut into
         `chunks` sub-batches whose host->device copy, GPU work and device->host copy overlap on three
-        streams, so only the first upload and the last download are exposed.  Returns when every
-        download has been ordered on the current stream (synchronise it before reading host_out)."""
+        streams through two persistent device staging slots (no allocation inside the loop), so only the
+        first upload and the last download are exposed.  Returns when every download has been ordered on
+        the current stream (synchronise it before reading host_out)."""
         if host_in.is_cuda or host_out.is_cuda:
             raise RuntimeError("run_host takes host tensors; call the pipeline directly for device tensors")
-        B = host_in.shape[0]
+        B, N = host_in.shape
         Bc = -(-B // max(1, chunks))
         cur = torch.cuda.current_stream()
         dev = cur.device
-        if not hasattr(self, "_copy_streams"):
-            self._copy_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
-        s_in, s_out = self._copy_streams
+        st = getattr(self, "_host_state", None)
+        if st is None or st["key"] != (Bc, N, dev):
+            st = {"key": (Bc, N, dev), "s_in": torch.cuda.Stream(device=dev), "s_out": torch.cuda.Stream(device=dev),
+                  "d_in": [torch.empty(Bc, N, device=dev) for _ in range(2)],
+                  "d_out": [torch.empty(Bc, N, device=dev) for _ in range(2)],
+                  "consumed": [None, None], "drained": [None, None]}
+            self._host_state = st
+        s_in, s_out = st["s_in"], st["s_out"]
         s_in.wait_stream(cur)
         s_out.wait_stream(cur)
-        for c0 in range(0, B, Bc):
+        for i, c0 in enumerate(range(0, B, Bc)):
             sl = slice(c0, min(B, c0 + Bc))
+            n = sl.stop - sl.start
+            k = i & 1
+            d_in, d_out = st["d_in"][k][:n], st["d_out"][k][:n]
+            if st["consumed"][k] is not None:
+                s_in.wait_event(st["consumed"][k])          # the slot's previous input has been read by its STFT
             with torch.cuda.stream(s_in):
-                d_in = host_in[sl].to(dev, non_blocking=True)
+                d_in.copy_(host_in[sl], non_blocking=True)
                 e_in = torch.cuda.Event()
                 e_in.record(s_in)
             cur.wait_event(e_in)
-            d_in.record_stream(cur)
-            out = self(d_in)
+            if st["drained"][k] is not None:
+                cur.wait_event(st["drained"][k])            # the slot's previous output has been downloaded
+            self(d_in, wave_out=d_out)
             e_done = torch.cuda.Event()
             e_done.record(cur)
+            st["consumed"][k] = e_done
             s_out.wait_event(e_done)
             with torch.cuda.stream(s_out):
-                host_out[sl].copy_(out, non_blocking=True)
-            out.record_stream(s_out)
+                host_out[sl].copy_(d_out, non_blocking=True)
+                e_out = torch.cuda.Event()
+                e_out.record(s_out)
+            st["drained"][k] = e_out
         cur.wait_stream(s_out)
         return host_out

@@ -64,9 +64,35 @@ def spec_and_angle_from_wave(wave, n_fft, hop_length):
     return torch.cat([ops.transpose(lm), ops.transpose(ph)], 0).cpu().numpy()
 
 
-def griffin_lim(spec, n_fft, hop_length, n_iter):
-    """Griffin-Lim phase retrieval on the GPU (utils.py:85-134): n_iter x (STFT -> phase ->
-    ISTFT) with the STFT/ISTFT kernels.  ``spec`` is the DC-less magnitude ``[C, T]``.
+def griffin_lim_batch(mag_fm, n_fft, hop_length, n_iter, init=None, generator=None):
+    """Griffin-Lim on a batch, device tensors in and out: ``mag_fm`` float32 ``[B, T, C]`` (frame-major
+    DC-less magnitudes) -> (audio ``[B, (T-1)*hop]`` un-normalised, (re, im) of the last projected
+    spectrogram ``[B, T, C]``, per-clip RMSE between the last two iterates ``[B]``).  Each iteration is two
+    kernels: ``pg_stft_project`` (STFT with the magnitude replaced in its epilogue, X/|X| instead of
+    exp(j*angle X)) and ``pg_istft``; nothing leaves the GPU inside the loop."""
+    B, T, C = mag_fm.shape
+    if 2 * C != n_fft:
+        raise RuntimeError(f"griffin_lim: spec has {C} rows, expected n_fft/2 = {n_fft // 2}")
+    n = (T - 1) * hop_length
+    if init is None:
+        recon = torch.randn(B, n, device=mag_fm.device, dtype=torch.float32, generator=generator)
+    else:
+        recon = init.to(mag_fm.device, torch.float32).reshape(B, n).contiguous()
+    bufs = (torch.empty_like(mag_fm), torch.empty_like(mag_fm))
+    prev = recon
+    for _ in range(int(n_iter)):
+        re, im = ops.stft_project(recon, mag_fm, n_fft, hop_length, out=bufs)
+        prev = recon
+        recon, _ = ops.istft(re, im, PG_SPEC_CARTESIAN, n_fft, hop_length, normalize=False, check_finite=False)
+    loss = torch.sqrt(torch.sum((recon - prev) ** 2, dim=1) / n) if n_iter > 0 else None
+    return recon, (bufs if n_iter > 0 else None), loss
+
+
+def griffin_lim(spec, n_fft, hop_length, n_iter, init=None):
+    """Griffin-Lim phase retrieval on the GPU (utils.py:85-134): n_iter x (STFT -> keep phase, impose
+    ``spec`` -> ISTFT), then the finiteness check and peak normalisation of utils.py:131-132.  ``spec`` is
+    the DC-less magnitude ``[C, T]``; returns (audio, new_spec, loss) like the reference.  ``init``
+    (optional, ``[(T-1)*hop]``) replaces the random start vector of utils.py:116.
 
     Deviation, stated: the reference hands the DC-less matrix straight to librosa.istft
     (utils.py:114,127), which then infers n_fft' = 2*(C-1) (2046) -- a latent bug that keeps
@@ -78,26 +104,18 @@ def griffin_lim(spec, n_fft, hop_length, n_iter):
     if 2 * mag.shape[0] != n_fft:
         raise RuntimeError(f"griffin_lim: spec has {mag.shape[0]} rows, expected n_fft/2 = {n_fft // 2}")
     mag_fm = ops.transpose(mag.unsqueeze(0))                               # [1, T, C]
-    T = mag_fm.shape[1]
-    n = (T - 1) * hop_length
-    recon = torch.randn(1, n, device=dev, dtype=torch.float32)
-    loss = None
-    phase = None
-    for _ in range(int(n_iter)):
-        _, phase = ops.stft(recon, n_fft, hop_length, mode=PG_STFT_LOGMAG)
-        prev = recon
-        recon, _ = ops.istft(mag_fm, phase, PG_SPEC_POLAR_MAG, n_fft, hop_length, normalize=False, check_finite=False)
-        loss = torch.sqrt(torch.sum((recon - prev) ** 2 / recon.numel()))
+    if init is not None:
+        init = torch.from_numpy(np.ascontiguousarray(init, dtype=np.float32)).view(1, -1)
+    recon, planes, loss = griffin_lim_batch(mag_fm, n_fft, hop_length, n_iter, init=init)
     if not bool(torch.isfinite(recon).all()):
         raise ValueError("Audio buffer is not finite everywhere")
     peak = recon.abs().max()
     if float(peak) >= np.finfo(np.float32).tiny:
         recon = recon / peak
     new_spec = None
-    if phase is not None:
-        ph = ops.transpose(phase)[0].cpu().numpy()
-        new_spec = np.asarray(spec) * np.exp(1.0j * ph)
-    return recon[0].cpu().numpy(), new_spec, (float(loss) if loss is not None else None)
+    if planes is not None:
+        new_spec = (ops.transpose(planes[0])[0] + 1j * ops.transpose(planes[1])[0]).cpu().numpy()
+    return recon[0].cpu().numpy(), new_spec, (float(loss[0]) if loss is not None else None)
 
 
 # ------------------------------------------------------------------ plotting (utils.py:46-83,136-143)
