@@ -205,21 +205,51 @@ __global__ void unpack_grad_kernel(const float* __restrict__ packed, int transpo
 }
 
 // ------------------------------------------------------------------------------------ Adam
+__device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v, float lr_bc1, float b1, float b2, float eps,
+                                          float bc2_sqrt_inv, float grad_scale) {
+    const float gi = g * grad_scale;
+    m = b1 * m + (1.f - b1) * gi;
+    v = b2 * v + (1.f - b2) * gi * gi;
+    // torch.optim.Adam: p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
+    p = p - lr_bc1 * m / (sqrtf(v) * bc2_sqrt_inv + eps);
+    return p;
+}
+
+// HBM-bound: 16 B read + 12 B written per parameter (+2..4 B of refreshed operand planes); 128-bit accesses.
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
             float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale,
-            __nv_bfloat16* __restrict__ w_hi, __nv_bfloat16* __restrict__ w_lo) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float gi = g[i] * grad_scale;
-        const float mi = b1 * m[i] + (1.f - b1) * gi;
-        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi; v[i] = vi;
-        // torch.optim.Adam: p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
-        const float pi = p[i] - (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
-        p[i] = pi;
+            uint16_t* __restrict__ w_hi, uint16_t* __restrict__ w_lo) {
+    const float lr_bc1 = lr / bc1, bc2_sqrt_inv = 1.f / bc2_sqrt;
+    const size_t n4 = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                        reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo)) & 7) == 0 ? n / 4 : 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 pi = reinterpret_cast<float4*>(p)[i];
+        const float4 gi = __ldg(reinterpret_cast<const float4*>(g) + i);
+        float4 mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i];
+        adam_one(pi.x, gi.x, mi.x, vi.x, lr_bc1, b1, b2, eps, bc2_sqrt_inv, grad_scale);
+        adam_one(pi.y, gi.y, mi.y, vi.y, lr_bc1, b1, b2, eps, bc2_sqrt_inv, grad_scale);
+        adam_one(pi.z, gi.z, mi.z, vi.z, lr_bc1, b1, b2, eps, bc2_sqrt_inv, grad_scale);
+        adam_one(pi.w, gi.w, mi.w, vi.w, lr_bc1, b1, b2, eps, bc2_sqrt_inv, grad_scale);
+        reinterpret_cast<float4*>(p)[i] = pi;
+        reinterpret_cast<float4*>(m)[i] = mi;
+        reinterpret_cast<float4*>(v)[i] = vi;
         if (w_hi) {
-            __nv_bfloat16 h, l;
-            split_bf16(pi, h, l);
+            __align__(8) uint16_t h[4], l[4];
+            split16(pi.x, PG_FMT_BF16, h[0], l[0]); split16(pi.y, PG_FMT_BF16, h[1], l[1]);
+            split16(pi.z, PG_FMT_BF16, h[2], l[2]); split16(pi.w, PG_FMT_BF16, h[3], l[3]);
+            reinterpret_cast<uint2*>(w_hi)[i] = *reinterpret_cast<uint2*>(h);
+            if (w_lo) reinterpret_cast<uint2*>(w_lo)[i] = *reinterpret_cast<uint2*>(l);
+        }
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float pi = p[i], mi = m[i], vi = v[i];
+        adam_one(pi, g[i], mi, vi, lr_bc1, b1, b2, eps, bc2_sqrt_inv, grad_scale);
+        p[i] = pi; m[i] = mi; v[i] = vi;
+        if (w_hi) {
+            uint16_t h, l;
+            split16(pi, PG_FMT_BF16, h, l);
             w_hi[i] = h;
             if (w_lo) w_lo[i] = l;
         }
@@ -297,8 +327,7 @@ extern "C" int pg_adam_step(float* p, const float* g, float* m, float* v, int64_
     PG_REQUIRE(p && g && m && v && n > 0 && step >= 1, "pg_adam_step: bad arguments");
     const float bc1 = 1.f - powf(beta1, (float)step);
     const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
-    int gx = (int)((n + 255) / 256); if (gx > 148 * 32) gx = 148 * 32;
-    adam_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale,
-                                                                             reinterpret_cast<__nv_bfloat16*>(w_hi), reinterpret_cast<__nv_bfloat16*>(w_lo));
+    int gx = (int)((n / 4 + 255) / 256); if (gx > 148 * 16) gx = 148 * 16; if (gx < 1) gx = 1;
+    adam_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale, w_hi, w_lo);
     return check_launch("adam_kernel");
 }
