@@ -40,7 +40,7 @@ int pg_check_device(int* sm_count, int* cc_major, int* cc_minor);
  * 16-bit hi/lo planes (op_fmt: PG_FMT_BF16 or PG_FMT_F16) [B][..][n_fft/2] with op_batch_stride
  * elements between clips -- the operand of the first convolution.  twiddle: float2[n_fft] = exp(-2*pi*i*m/n_fft).
  * n_fft in {256,512,1024,2048}, hop = n_fft/4. */
-enum { PG_STFT_LOGMAG = 0, PG_STFT_REIM = 1, PG_STFT_PROJECT = 2 /* pg_stft_project only */ };
+enum { PG_STFT_LOGMAG = 0, PG_STFT_REIM = 1, PG_STFT_PROJECT = 2 /* pg_stft_project only */, PG_STFT_PAIRS = 3 /* pg_stft_pairs only */ };
 int pg_stft_num_frames(int n_samples, int hop);
 int pg_stft(const float* wave, int B, int N, int n_fft, int hop, const float* twiddle, int mode,
             float* out_a, float* out_b, uint16_t* op_hi, uint16_t* op_lo, int64_t op_batch_stride,
@@ -52,13 +52,19 @@ int pg_stft(const float* wave, int B, int N, int n_fft, int hop, const float* tw
 int pg_stft_project(const float* wave, int B, int N, int n_fft, int hop, const float* twiddle,
                     const float* mag, float* out_re, float* out_im, pg_stream stream);
 
+/* Online training-pair producer: the STFT of preproc_mdb.py:93-96, the dataset-wide standardisation of the (re, im)
+ * values (preproc_mdb.py:182: (x - mean) / std) and data.py:39-47 (log1p|.|, angle) in one kernel:
+ * wave [B][N] -> log-magnitude and phase planes [B][T][n_fft/2], the channels-last pair TrainStep consumes. */
+int pg_stft_pairs(const float* wave, int B, int N, int n_fft, int hop, const float* twiddle, float mean, float std,
+                  float* out_logmag, float* out_phase, pg_stream stream);
+
 /* ---------------------------------------------------------------- ISTFT back end
  * Replaces utils.generate_audio (utils.py:11-44): zero DC row (:38-39), librosa.istft (:40:
  * inverse real FFT, periodic Hann, overlap-add, / window sum-of-squares, trim n_fft/2),
  * finiteness check (:41 -> nonfinite[b] != 0), peak normalisation (:42 -> pg_peak_normalize),
  * with the polar->complex step of demo.py:39 / train.py:83 fused in (PG_SPEC_POLAR_LOG:
  * a = log1p-magnitude, b = phase; PG_SPEC_CARTESIAN: a = re, b = im; PG_SPEC_POLAR_MAG:
- * a = magnitude, b = phase or NULL for zero phase).  Inputs frame-major [B][T][n_fft/2]
+ * a = magnitude; in both polar modes b may be NULL for zero phase: the "no phase" reconstruction of train.py:86).  Inputs frame-major [B][T][n_fft/2]
  * (bins 1..n_fft/2); wave [B][(T-1)*hop].  peak [B] (max |wave|) and nonfinite [B] may be NULL. */
 enum { PG_SPEC_POLAR_LOG = 0, PG_SPEC_CARTESIAN = 1, PG_SPEC_POLAR_MAG = 2 };
 int pg_istft(const float* in_a, const float* in_b, int mode, int B, int T, int n_fft, int hop,

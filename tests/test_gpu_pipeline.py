@@ -115,3 +115,76 @@ def test_host_buffer_call_equals_device_call():
     torch.cuda.synchronize()
     ref = torch.cat([pipe(h_in[i:i + 3].cuda()).cpu() for i in range(0, B, 3)])
     assert torch.equal(h_out, ref)
+
+
+def test_online_training_pairs_match_the_offline_stage():
+    """datapath.TrainingPairProducer vs preproc_mdb.py:66-97,182 + data.py:39-47 restated with the numpy oracle."""
+    from phasegen.datapath import TrainingPairProducer, chunk_starts
+    from oracle import stft_np
+    n_fft, hop, t_slice = 512, 128, 127 * 128
+    rng = np.random.default_rng(3)
+    audio = (0.3 * rng.standard_normal(5 * t_slice + 1000)).astype(np.float32)
+    starts = chunk_starts(len(audio), t_slice, 1, np.random.default_rng(4))
+    assert starts[0] == 0 and len(starts) == 2 * 6 and starts.max() + t_slice > len(audio)   # the last regular chunk is padded
+    prod = TrainingPairProducer(audio, t_slice, n_fft, hop)
+    assert prod.frames == 128
+    # oracle: chunk, zero pad, STFT, drop DC, standardise re/im over the whole set, log1p|.|, angle
+    specs = []
+    for s0 in starts:
+        c = audio[s0:s0 + t_slice].astype(np.float64)
+        c = np.pad(c, (0, t_slice - len(c)))
+        specs.append(stft_np.stft(c, n_fft, hop)[1:])
+    S = np.stack(specs)
+    vals = np.stack([S.real, S.imag], 1)
+    mean, std = vals.mean(), vals.std()
+    m_gpu, s_gpu = prod.stats(starts, batch=5)
+    assert abs(m_gpu - mean) < 1e-5 * std and abs(s_gpu - std) < 1e-5 * std
+    Z = (S.real - mean) / std + 1j * (S.imag - mean) / std
+    lm, ph = prod.pairs(starts, mean, std)
+    assert lm.shape == (len(starts), 128, n_fft // 2)
+    lm = lm.cpu().numpy().transpose(0, 2, 1); ph = ph.cpu().numpy().transpose(0, 2, 1)
+    assert rel_l2(lm, np.log1p(np.abs(Z))) < 1e-4
+    Zg = np.expm1(lm) * np.exp(1j * ph)
+    assert np.linalg.norm(Zg - Z) / np.linalg.norm(Z) < 1e-4
+
+
+def test_validation_report_matches_the_reference_loop():
+    """phasegen.validate vs train.py:69-122 restated with the oracle (hybrid / no-phase / Griffin-Lim audio)."""
+    import model
+    from oracle import stft_np, unet_torch
+    from phasegen import synth
+    from phasegen.validate import validation_report
+    C, T, V = 128, 40, 2
+    n_fft, hop = 2 * C, C // 2
+    torch.manual_seed(9)
+    net = model.UNetModel(C, 2 * C).cuda()
+    synth.randomize_norm_affine(net, seed=9)
+    net.precision = "fp32_simt"
+    rng = np.random.default_rng(9)
+    vals = []
+    for _ in range(V):
+        S = stft_np.stft(rng.standard_normal((T - 1) * hop), n_fft, hop)[1:]
+        vals.append(np.stack([np.log1p(np.abs(S)), np.angle(S)]))
+    val = np.stack(vals).astype(np.float32)
+    init = rng.standard_normal((V, (T - 1) * hop)).astype(np.float32)
+    n_it = 5
+    rep = validation_report(net, val, n_fft, hop, gl_iters=n_it, gl_init=torch.from_numpy(init), return_audio=True)
+    sd = {k: v.detach().cpu() for k, v in net.model.state_dict().items()}
+    mses, nops, lims = [], [], []
+    for v in range(V):
+        lm, ph = val[v, 0].astype(np.float64), val[v, 1].astype(np.float64)
+        pred = unet_torch.unet_forward(sd, torch.from_numpy(lm)[None], torch.float64, per_clip_bn=True)[0, :C].numpy()
+        mag = np.expm1(lm)
+        orig = stft_np.generate_audio(mag * np.exp(1j * ph), 0, hop, is_stft=True)
+        hyb = stft_np.generate_audio(mag * np.exp(1j * pred), 0, hop, is_stft=True)
+        nop = stft_np.generate_audio(mag.astype(np.complex128), 0, hop, is_stft=True)
+        recon = init[v].astype(np.float64)
+        for _ in range(n_it):
+            rs = stft_np.stft(recon, n_fft, hop)[1:]
+            recon = stft_np.istft(np.concatenate([np.zeros((1, T)), mag * np.exp(1j * np.angle(rs))]), hop)
+        lim = stft_np.peak_normalize(recon)
+        assert rel_l2(rep["audio"]["hybrid"][v].cpu().numpy(), hyb) < 1e-3
+        mses.extend(np.abs(orig - hyb)); nops.extend(np.abs(orig - nop)); lims.extend(np.abs(orig - lim))
+    assert abs(rep["MSE"] - np.mean(mses)) < 2e-3 * np.mean(mses)
+    assert abs(rep["NOPMSE"] - np.mean(nops)) < 1e-3 * np.mean(nops)
+    assert abs(rep["LMSE"] - np.mean(lims)) < 1e-3 * np.mean(lims)

@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(kStftThreads)
 stft_kernel(const float* __restrict__ wave, int N, int T, const float2* __restrict__ tw_g, int mode,
             float* __restrict__ out_a, float* __restrict__ out_b,
             uint16_t* __restrict__ op_hi, uint16_t* __restrict__ op_lo,
-            long long op_batch_stride, int op_fmt, int frames_per_cta, const float* __restrict__ proj_mag) {
+            long long op_batch_stride, int op_fmt, int frames_per_cta, const float* __restrict__ proj_mag,
+            float std_mean, float std_inv) {
     using Cfg = FrameCfg<NC>;
     using R = Radix<NC, false>;
     extern __shared__ float2 smem2[];
@@ -146,7 +147,11 @@ stft_kernel(const float* __restrict__ wave, int N, int T, const float2* __restri
                 const float g = __ldg(proj_mag + row + bin - 1);
                 a = m2 > 0.f ? g * x.x * inv : g;
                 ph = g * x.y * inv;
-            } else if (mode == PG_STFT_LOGMAG) {
+            } else if (mode == PG_STFT_LOGMAG || mode == PG_STFT_PAIRS) {
+                if (mode == PG_STFT_PAIRS) {                // global standardisation of (re, im): preproc_mdb.py:182
+                    x.x = (x.x - std_mean) * std_inv;
+                    x.y = (x.y - std_mean) * std_inv;
+                }
                 a = fast_log1p_mag(x.x, x.y);
                 if (out_b) ph = atan2f(x.y, x.x);
             } else {
@@ -321,7 +326,8 @@ __global__ void peak_normalize_kernel(float* __restrict__ wave, const unsigned* 
 
 template <int NC>
 static int launch_stft(const float* wave, int B, int N, int T, const float* tw, int mode, float* a, float* bq,
-                       uint16_t* hi, uint16_t* lo, long long bs, int fmt, cudaStream_t st, const float* proj_mag = nullptr) {
+                       uint16_t* hi, uint16_t* lo, long long bs, int fmt, cudaStream_t st, const float* proj_mag = nullptr,
+                       float std_mean = 0.f, float std_inv = 1.f) {
     using Cfg = FrameCfg<NC>;
     const bool fast = mode == PG_STFT_LOGMAG && a && !bq && hi && lo;
     auto k = !fast ? stft_kernel<NC, 0> : fmt == PG_FMT_F16 ? stft_kernel<NC, 2> : stft_kernel<NC, 1>;
@@ -335,7 +341,7 @@ static int launch_stft(const float* wave, int B, int N, int T, const float* tw, 
     }
     const int frames_per_cta = Cfg::FC * 4;                 // tables are built once per 4 passes over the frame slots
     dim3 grid((T + frames_per_cta - 1) / frames_per_cta, B);
-    k<<<grid, kStftThreads, sm, st>>>(wave, N, T, reinterpret_cast<const float2*>(tw), mode, a, bq, hi, lo, bs, fmt, frames_per_cta, proj_mag);
+    k<<<grid, kStftThreads, sm, st>>>(wave, N, T, reinterpret_cast<const float2*>(tw), mode, a, bq, hi, lo, bs, fmt, frames_per_cta, proj_mag, std_mean, std_inv);
     return check_launch("stft_kernel");
 }
 
@@ -401,12 +407,31 @@ extern "C" int pg_stft_project(const float* wave, int B, int N, int n_fft, int h
     return PG_ERR_UNSUPPORTED;
 }
 
+extern "C" int pg_stft_pairs(const float* wave, int B, int N, int n_fft, int hop, const float* twiddle, float mean, float std,
+                             float* out_logmag, float* out_phase, pg_stream stream) {
+    PG_REQUIRE(wave && twiddle && out_logmag && out_phase && B > 0 && N > 0, "pg_stft_pairs: null pointer or empty batch");
+    PG_REQUIRE(hop * 4 == n_fft, "pg_stft_pairs: hop must be n_fft/4 (got n_fft=%d hop=%d)", n_fft, hop);
+    PG_REQUIRE(N > n_fft / 2, "pg_stft_pairs: reflect padding needs more than n_fft/2 samples (N=%d)", N);
+    PG_REQUIRE(std > 0.f && B <= 65535, "pg_stft_pairs: std must be positive and B <= 65535");
+    const int T = 1 + N / hop;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const float inv = 1.0f / std;
+    switch (n_fft) {
+        case 256:  return pg::launch_stft<128>(wave, B, N, T, twiddle, PG_STFT_PAIRS, out_logmag, out_phase, nullptr, nullptr, 0, 0, st, nullptr, mean, inv);
+        case 512:  return pg::launch_stft<256>(wave, B, N, T, twiddle, PG_STFT_PAIRS, out_logmag, out_phase, nullptr, nullptr, 0, 0, st, nullptr, mean, inv);
+        case 1024: return pg::launch_stft<512>(wave, B, N, T, twiddle, PG_STFT_PAIRS, out_logmag, out_phase, nullptr, nullptr, 0, 0, st, nullptr, mean, inv);
+        case 2048: return pg::launch_stft<1024>(wave, B, N, T, twiddle, PG_STFT_PAIRS, out_logmag, out_phase, nullptr, nullptr, 0, 0, st, nullptr, mean, inv);
+    }
+    pg::set_error("pg_stft_pairs: n_fft must be 256, 512, 1024 or 2048 (got %d)", n_fft);
+    return PG_ERR_UNSUPPORTED;
+}
+
 extern "C" int pg_istft(const float* in_a, const float* in_b, int mode, int B, int T, int n_fft, int hop,
                         const float* twiddle, float* wave, float* peak, int* nonfinite, pg_stream stream) {
     PG_REQUIRE(in_a && twiddle && wave && B > 0 && T > 1, "pg_istft: null pointer or empty input");
     PG_REQUIRE(hop * 4 == n_fft, "pg_istft: hop must be n_fft/4 (got n_fft=%d hop=%d)", n_fft, hop);
     PG_REQUIRE(mode >= PG_SPEC_POLAR_LOG && mode <= PG_SPEC_POLAR_MAG, "pg_istft: bad mode %d", mode);
-    PG_REQUIRE(in_b || mode == PG_SPEC_POLAR_MAG, "pg_istft: second plane missing");
+    PG_REQUIRE(in_b || mode != PG_SPEC_CARTESIAN, "pg_istft: second plane missing");   // polar modes: NULL phase = zero phase
     PG_REQUIRE(B <= 65535, "pg_istft: batch too large for one launch");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (peak) cudaMemsetAsync(peak, 0, sizeof(float) * B, st);

@@ -13,7 +13,7 @@ PG_CONV, PG_CONV_TRANSPOSE = 0, 1
 PG_PREC_FP32_SIMT, PG_PREC_BF16X3, PG_PREC_BF16, PG_PREC_F16X3, PG_PREC_F16X2 = 0, 1, 2, 3, 4
 PG_DT_NONE, PG_DT_F32, PG_DT_BF16_SPLIT, PG_DT_BF16, PG_DT_F16_SPLIT, PG_DT_F16 = 0, 1, 2, 3, 4, 5
 PG_FMT_BF16, PG_FMT_F16 = 0, 1
-PG_STFT_LOGMAG, PG_STFT_REIM = 0, 1
+PG_STFT_LOGMAG, PG_STFT_REIM, PG_STFT_PROJECT, PG_STFT_PAIRS = 0, 1, 2, 3
 PG_SPEC_POLAR_LOG, PG_SPEC_CARTESIAN, PG_SPEC_POLAR_MAG = 0, 1, 2
 
 # "f16mix" is an executor-level name (phasegen/unet.py): fp16 planes everywhere, the three-product
@@ -46,6 +46,7 @@ _SIGNATURES = {
     "pg_stft_num_frames": (_I, [_I, _I]),
     "pg_stft": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _L, _I, _P]),
     "pg_stft_project": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "pg_stft_pairs": (_I, [_P, _I, _I, _I, _I, _P, _F, _F, _P, _P, _P]),
     "pg_istft": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "pg_peak_normalize": (_I, [_P, _P, _I, _I, _P]),
     "pg_pack_weight": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),

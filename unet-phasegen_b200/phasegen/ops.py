@@ -94,6 +94,20 @@ def stft_project(wave, mag, n_fft, hop, out=None):
     return re, im
 
 
+def stft_pairs(wave, n_fft, hop, mean=0.0, std=1.0):
+    """wave [B,N] -> (log1p|X'|, angle X') fp32 [B,T,C] with X' = (X - mean(1+j)) / std: the STFT of
+    preproc_mdb.py:93-96, the dataset standardisation of :182 and data.py:39-47 in one kernel."""
+    check_stft_geometry(n_fft, hop)
+    wave = _need_cuda(wave, "wave")
+    B, N = wave.shape
+    T = 1 + N // hop
+    lm = torch.empty(B, T, n_fft // 2, device=wave.device, dtype=torch.float32)
+    ph = torch.empty_like(lm)
+    _lib.call("pg_stft_pairs", _ptr(wave), B, N, n_fft, hop, _ptr(twiddle(n_fft, wave.device)), float(mean), float(std),
+              _ptr(lm), _ptr(ph), _stream())
+    return lm, ph
+
+
 def istft(a, b, mode, n_fft, hop, normalize=True, check_finite=True, out=None):
     """(a, b) fp32 [B,T,n_fft/2] frame-major -> wave [B,(T-1)*hop]; optional peak normalisation
     (utils.py:42) and finiteness check (utils.py:41; costs one device->host sync)."""
