@@ -164,13 +164,15 @@ static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
             }
             p->merged = 1; p->nb = best_nb; p->strip_rows = strip_full;
             // Two MMAs (2 x up to 256 accumulator columns, one TMEM stage) per weight tile while that still leaves
-            // a tile for every CTA (pair): the weight stream from L2 -- the bound of these layers, whose
+            // a tile for >= 80 % of the CTA pairs: the weight stream from L2 -- the bound of these layers, whose
             // weights are read once per tile -- halves.
             const long tiles2 = (long)slabs * ((d->B + 2 * best_nb - 1) / (2 * best_nb));
             const char* g2 = getenv("PG_TC_MGROUPS");
             const int planes_b = (d->precision == PG_PREC_BF16X3 || d->precision == PG_PREC_F16X3 || d->precision == PG_PREC_F16X2) ? 2 : 1;
             const long slot_bytes = (long)planes_b * (2 * best_nb / (p->pair ? 2 : 1)) * strip_full * 128;   // per CTA, one strip slot
-            if (2 * best_nb <= d->B && 2 * best_nb * strip_full <= 512 && tiles2 >= units && 2 * slot_bytes <= 120 * 1024 &&
+            const char* fr = getenv("PG_TC_MG_FRAC");           // experiment hook: fraction of the grid two-group tiles must fill
+            const double need = (fr ? atof(fr) : 0.8) * units;    // 0.8: measured optimum (profiles/r01_conv_mgroups_ab.log)
+            if (2 * best_nb <= d->B && 2 * best_nb * strip_full <= 512 && (double)tiles2 >= need && 2 * slot_bytes <= 120 * 1024 &&
                 !(g2 && atoi(g2) == 1)) {
                 p->mgroups = 2; p->nb = 2 * best_nb;
             }
