@@ -213,3 +213,33 @@ def test_native_train_step_tracks_reference_loop():
     assert ref_losses[2] < ref_losses[0]
     w = net.model.state_dict()["model.3.weight"].cpu().double()
     assert rel_l2(w.numpy(), leaf["model.3.weight"].detach().numpy()) < 1e-4
+
+
+def test_optimizer_state_round_trip_resumes_identically(tmp_path):
+    """TrainStep.state_dict()/load_state_dict(): a run resumed from (model checkpoint, optimiser state) continues
+    bit-identically to the uninterrupted one, and the state file is in the torch layout of each parameter."""
+    import model
+    from phasegen.train import TrainStep
+    C, T, B = 64, 32, 4
+    torch.manual_seed(21)
+    lm = torch.rand(B, T, C, device="cuda") * 3
+    ph = (torch.rand(B, T, C, device="cuda") - 0.5) * 6
+    net = model.UNetModel(C, 2 * C).cuda()
+    step = TrainStep(net, B, T, "cuda", precision="bf16x3")
+    for _ in range(3):
+        step(lm, ph)
+    ck = str(tmp_path / "ckpt")
+    net.save(ck)
+    opt = step.state_dict()
+    torch.save(opt, str(tmp_path / "opt"))
+    assert opt["step"] == 3
+    w = dict(net.model.named_parameters())
+    for name, st in opt["state"].items():
+        assert tuple(st["exp_avg"].shape) == tuple(w[name].shape), name
+    a = [float(step(lm, ph)[0]) for _ in range(3)]
+    net2 = model.UNetModel(C, 2 * C).cuda()
+    net2.load(ck)
+    step2 = TrainStep(net2, B, T, "cuda", precision="bf16x3")
+    step2.load_state_dict(torch.load(str(tmp_path / "opt")))
+    b = [float(step2(lm, ph)[0]) for _ in range(3)]
+    assert a == b

@@ -25,11 +25,12 @@ struct WgradParams {
     int n_mchunks;
     int n_stages;
     int n_terms;
-    int a_plane, b_plane;   // bytes of one precision plane of A (2 co blocks) / B (nci/64 ci blocks)
+    int a_plane, b_plane;   // bytes of one precision plane of A (2 co blocks) / B (nci/64 ci blocks; half of them per CTA of a pair)
+    int pair;               // work items are 256 output channels wide, owned by a CTA pair (cta_group::2, see conv_tc.cu)
 };
 
 constexpr int kWgThreads = 192;
-constexpr int kWgMaxStages = 4;
+constexpr int kWgMaxStages = 6;
 
 struct WgItem { int co_tile, ci_tile, phase, group; };
 
@@ -39,13 +40,14 @@ __device__ __forceinline__ WgItem wg_decode(const WgradParams& p, int item) {
     const int n_citiles = pl.C_in / p.nci;
     WgItem w;
     int g = item % n_groups; item /= n_groups;
-    w.ci_tile = item % n_citiles; w.co_tile = item / n_citiles;
+    w.ci_tile = item % n_citiles; w.co_tile = item / n_citiles;     // pair mode: co_tile counts 256-channel slabs
     w.phase = 0;
     if (g >= pl.n_groups[0]) { g -= pl.n_groups[0]; w.phase = 1; }
     w.group = g;
     return w;
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
                 const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
@@ -66,56 +68,71 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
     // shuffled warp index: provably warp-uniform role branches (see conv_tc.cu)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int n_groups = pl.n_groups[0] + pl.n_groups[1];
-    const int n_items = pl.n_cotiles * (pl.C_in / prm.nci) * n_groups;
+    const int n_items = (PAIR ? pl.n_cotiles / 2 : pl.n_cotiles) * (pl.C_in / prm.nci) * n_groups;
     const int n_kchunks = pl.B * prm.n_mchunks;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_g_hi); tma_prefetch_desc(&map_x_hi);
         for (int i = 0; i < prm.n_stages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-        mbar_init(accFull, 1); mbar_init(accEmpty, 4);
+        mbar_init(accFull, 1); mbar_init(accEmpty, PAIR ? 8 : 4);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) { if (PAIR) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;
+    const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_bblk = PAIR ? prm.nci / 128 : prm.nci / 64;       // 64-channel X blocks this CTA loads
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
             const uint32_t bytes = (uint32_t)stage_bytes;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int item = item0; item < n_items; item += item_step) {
                 const WgItem w = wg_decode(prm, item);
                 const ConvGroup grp = pl.groups[w.phase][w.group];
                 for (int kc = 0; kc < n_kchunks; ++kc, ++it) {
                     const int b = kc / prm.n_mchunks, m0 = (kc % prm.n_mchunks) * prm.R;
                     const int s = it % prm.n_stages; const uint32_t ph = (it / prm.n_stages) & 1;
                     mbar_wait(empty + s, ph ^ 1);
-                    mbar_expect_tx(full + s, bytes);
+                    if (!PAIR) mbar_expect_tx(full + s, bytes);
+                    else if (rank == 0) mbar_expect_tx(full + s, 2 * bytes);      // both CTAs' operands
                     uint8_t* st = smem + (size_t)s * stage_bytes;
+                    const int co0 = (PAIR ? w.co_tile * 2 + rank : w.co_tile) * 128;
+                    const int ci0 = w.ci_tile * prm.nci + (PAIR ? rank * (prm.nci / 2) : 0);
                     for (int pln = 0; pln < planes; ++pln) {
                         const CUtensorMap* mg = pln ? &map_g_lo : &map_g_hi;
                         const CUtensorMap* mx = pln ? &map_x_lo : &map_x_hi;
                         uint8_t* a = st + (size_t)pln * prm.a_plane;
                         uint8_t* bq = st + (size_t)planes * prm.a_plane + (size_t)pln * prm.b_plane;
-                        for (int h = 0; h < 2; ++h)
-                            tma_load_4d(a + (size_t)h * prm.R * 128, mg, full + s, w.co_tile * 128 + h * 64, w.phase, m0, b);
-                        for (int h = 0; h < prm.nci / 64; ++h)
-                            tma_load_4d(bq + (size_t)h * prm.RB * 128, mx, full + s, w.ci_tile * prm.nci + h * 64, grp.parity,
-                                        m0 + grp.row0, b);
+                        for (int h = 0; h < 2; ++h) {
+                            if (PAIR) tma_load_4d_pair(a + (size_t)h * prm.R * 128, mg, full + s, co0 + h * 64, w.phase, m0, b);
+                            else tma_load_4d(a + (size_t)h * prm.R * 128, mg, full + s, co0 + h * 64, w.phase, m0, b);
+                        }
+                        for (int h = 0; h < n_bblk; ++h) {
+                            if (PAIR) tma_load_4d_pair(bq + (size_t)h * prm.RB * 128, mx, full + s, ci0 + h * 64, grp.parity, m0 + grp.row0, b);
+                            else tma_load_4d(bq + (size_t)h * prm.RB * 128, mx, full + s, ci0 + h * 64, grp.parity, m0 + grp.row0, b);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        {   // whole warp, warp-uniform control flow; one elected lane issues the tcgen05 instructions
+        if (rank == 0) {   // whole warp, warp-uniform control flow; one elected lane issues the tcgen05 instructions
             uint32_t it = 0, n_it = 0;
-            const uint32_t idesc = make_idesc_bf16_mn(prm.nci);
-            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc_flag) { if (elect_one()) umma_bf16(d, da, db, idesc, acc_flag); };
-            auto commit = [&](uint64_t* bar) { if (elect_one()) umma_commit(bar); __syncwarp(); };
+            const uint32_t idesc = (make_idesc_bf16_mn(prm.nci) & ~(0x1Fu << 24)) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);   // M = 256 for pairs
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc_flag) {
+                if (elect_one()) { if (PAIR) umma_bf16_pair(d, da, db, idesc, acc_flag); else umma_bf16(d, da, db, idesc, acc_flag); }
+            };
+            auto commit = [&](uint64_t* bar) {
+                if (elect_one()) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); }
+                __syncwarp();
+            };
             const uint32_t lbo_a = (uint32_t)prm.R * 128u, lbo_b = (uint32_t)prm.RB * 128u;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_it) {
+            for (int item = item0; item < n_items; item += item_step, ++n_it) {
                 const WgItem w = wg_decode(prm, item);
                 const ConvGroup grp = pl.groups[w.phase][w.group];
                 mbar_wait_sleep(accEmpty, (n_it & 1) ^ 1, 200);
@@ -154,12 +171,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
     } else {
         const int q = warp & 3;
         uint32_t n_it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_it) {
+        for (int item = item0; item < n_items; item += item_step, ++n_it) {
             const WgItem w = wg_decode(prm, item);
             const ConvGroup grp = pl.groups[w.phase][w.group];
             mbar_wait_sleep(accFull, n_it & 1, 1000);
             tc_fence_after();
-            const int co = w.co_tile * 128 + q * 32 + lane;
+            const int co = (PAIR ? w.co_tile * 2 + rank : w.co_tile) * 128 + q * 32 + lane;
             for (int j = 0; j < grp.n_taps; ++j) {
                 const ConvTap tp = pl.taps[w.phase][grp.first_tap + j];
                 float* dst = prm.dw + ((size_t)tp.w_idx * pl.C_out + co) * pl.C_in + (size_t)w.ci_tile * prm.nci;
@@ -174,12 +191,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(accEmpty);
+            if (lane == 0) { if (PAIR) mbar_arrive_leader(accEmpty); else mbar_arrive(accEmpty); }
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (PAIR) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) { tc_fence_after(); if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace pg
@@ -204,13 +221,20 @@ extern "C" int pg_wgrad_tc(const pg_conv_desc* d, const uint16_t* x_hi, const ui
     prm.dw = dw_packed;
     prm.n_terms = three ? 3 : 1;
     prm.nci = d->C_in % 128 == 0 ? 128 : 64;
+    {
+        int want = d->tc_cta_pair;
+        if (const char* e = getenv("PG_WG_PAIR")) want = atoi(e);   // A/B hook: 1 = single CTAs
+        // opt-in only (tc_cta_pair = 2): measured neutral-to-slightly-slower than single CTAs at the train shapes
+        // (12.46 vs 12.29 ms per step) -- this kernel is not bound by its shared-memory operand reads
+        prm.pair = (want == 2 && prm.nci == 128 && d->C_out % 256 == 0) ? 1 : 0;
+    }
     const int l_max = (pl.L_out + pl.OS - 1) / pl.OS;
     const int r_cap = three ? 64 : 128;
     prm.n_mchunks = (l_max + r_cap - 1) / r_cap;
     prm.R = ((l_max + prm.n_mchunks - 1) / prm.n_mchunks + 15) / 16 * 16;
     prm.RB = prm.R + 8;
     prm.a_plane = 2 * prm.R * 128;
-    prm.b_plane = (prm.nci / 64) * prm.RB * 128;
+    prm.b_plane = (prm.nci / 64 / (prm.pair ? 2 : 1)) * prm.RB * 128;
     const int planes = three ? 2 : 1;
     const int stage_bytes = planes * (prm.a_plane + prm.b_plane);
     int n_stages = (max_smem - 2048) / stage_bytes;
@@ -238,15 +262,29 @@ extern "C" int pg_wgrad_tc(const pg_conv_desc* d, const uint16_t* x_hi, const ui
         if ((rc = encode_bf16_map(&mx_hi, x_hi, 4, dims, str, box, "x_hi")) != PG_OK) return rc;
         if ((rc = encode_bf16_map(&mx_lo, three ? x_lo : x_hi, 4, dims, str, box, "x_lo")) != PG_OK) return rc;
     }
-    static size_t configured = 0;
-    if (smem_bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    const bool pair = prm.pair != 0;
+    static size_t configured[2] = {0, 0};
+    if (smem_bytes > configured[pair]) {
+        cudaError_t e = pair ? cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)
+                             : cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) { set_error("wgrad_tc: cannot opt in to %zu bytes of shared memory: %s", smem_bytes, cudaGetErrorString(e)); return PG_ERR_CUDA; }
-        configured = smem_bytes;
+        configured[pair] = smem_bytes;
     }
-    const int n_items = pl.n_cotiles * (pl.C_in / prm.nci) * (pl.n_groups[0] + pl.n_groups[1]);
-    int grid = n_items < sm_count ? n_items : sm_count;
-    if (d->tc_max_ctas > 0 && grid > d->tc_max_ctas) grid = d->tc_max_ctas;
-    wgrad_tc_kernel<<<grid, kWgThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(mg_hi, mg_lo, mx_hi, mx_lo, prm);
+    const int n_items = (pair ? pl.n_cotiles / 2 : pl.n_cotiles) * (pl.C_in / prm.nci) * (pl.n_groups[0] + pl.n_groups[1]);
+    int units = pair ? sm_count / 2 : sm_count;
+    if (d->tc_max_ctas > 0 && units > (pair ? (d->tc_max_ctas + 1) / 2 : d->tc_max_ctas)) units = pair ? (d->tc_max_ctas + 1) / 2 : d->tc_max_ctas;
+    if (units > n_items) units = n_items;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pair ? 2 * units : units);
+    cfg.blockDim = dim3(kWgThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t le = pair ? cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<true>, mg_hi, mg_lo, mx_hi, mx_lo, prm)
+                          : cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<false>, mg_hi, mg_lo, mx_hi, mx_lo, prm);
+    if (le != cudaSuccess) { set_error("wgrad_tc_kernel launch failed: %s", cudaGetErrorString(le)); return PG_ERR_CUDA; }
     return check_launch("wgrad_tc_kernel");
 }

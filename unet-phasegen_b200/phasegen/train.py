@@ -212,3 +212,50 @@ class TrainStep:
             ex.pack_weights(ws[:len(blocks)], ws[len(blocks):])
         net._mark_packed(ex)
         return loss3
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def _named_items(self):
+        """Adam items keyed by the parameter's state_dict name (the reference's checkpoint keys, model.py:45-48)."""
+        by_ptr = {p.data_ptr(): n for n, p in self.net.model.named_parameters()}
+        out = []
+        for it in self.items:
+            name = by_ptr.get(it["p"].data_ptr())
+            if name is None:
+                raise RuntimeError("phasegen: optimiser item without a matching model parameter")
+            out.append((name, it))
+        return out
+
+    def _is_transposed(self, name):
+        mod = self.net.model.get_submodule(name.rsplit(".", 1)[0])
+        return isinstance(mod, torch.nn.ConvTranspose1d)
+
+    def state_dict(self):
+        """Optimiser state for resume: step count, hyper-parameters and the Adam moments in the TORCH layout of
+        each parameter (so the file does not depend on this build's packed storage order)."""
+        from ._lib import PG_CONV, PG_CONV_TRANSPOSE
+        params = dict(self.net.model.named_parameters())
+        state = {}
+        for name, it in self._named_items():
+            p = params[name]
+            m, v = it["m"], it["v"]
+            if m.dim() == 3:                      # conv weights: packed [k][C_out][C_in] -> torch layout
+                perm = (2, 1, 0) if self._is_transposed(name) else (1, 2, 0)
+                m, v = m.permute(*perm), v.permute(*perm)
+            state[name] = {"exp_avg": m.detach().cpu().contiguous(), "exp_avg_sq": v.detach().cpu().contiguous()}
+        return {"step": self.t, "lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "state": state}
+
+    def load_state_dict(self, sd):
+        params = dict(self.net.model.named_parameters())
+        for name, it in self._named_items():
+            if name not in sd["state"]:
+                raise KeyError(f"phasegen: optimiser state for '{name}' missing from the checkpoint")
+            p = params[name]
+            for key, dst in (("exp_avg", it["m"]), ("exp_avg_sq", it["v"])):
+                src = sd["state"][name][key].to(dst.device, torch.float32)
+                if tuple(src.shape) != tuple(p.shape):
+                    raise RuntimeError(f"phasegen: optimiser state '{name}.{key}' has shape {tuple(src.shape)}, expected {tuple(p.shape)}")
+                if dst.dim() == 3:
+                    src = src.permute(2, 1, 0) if self._is_transposed(name) else src.permute(2, 0, 1)
+                dst.copy_(src)
+        self.t = int(sd["step"])
+        self.lr, self.betas, self.eps = float(sd["lr"]), tuple(sd["betas"]), float(sd["eps"])
