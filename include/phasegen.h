@@ -172,14 +172,14 @@ int pg_bn_bwd(const float* z, int B, int L, int C, const float* scale_shift, con
 /* weight gradient, packed fp32 [k][C_out][C_in]; d describes the FORWARD convolution; x = its input
  * operand, g = dZ operand planes [B][g_rows][C_out]. */
 int pg_wgrad_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* g_hi,
-                const uint16_t* g_lo, int g_rows, float* dw_packed, pg_stream stream);
+                const uint16_t* g_lo, int g_rows, void* dw_packed, int dw_dtype /* PG_DT_F32 | PG_DT_BF16 */, pg_stream stream);
 int pg_wgrad_simt(const pg_conv_desc* d, const float* x, const float* g, int g_rows, float* dw_packed, pg_stream stream);
 /* packed [k][C_out][C_in] -> torch layout (Conv1d [C_out][C_in][k] / ConvTranspose1d [C_in][C_out][k]) */
 int pg_unpack_grad(const float* packed, int kind, int C_in, int C_out, int k, float* out, pg_stream stream);
 /* torch.optim.Adam semantics (bias-corrected, eps outside the sqrt), fp32 state; step >= 1.
  * w_hi / w_lo (may be NULL): also write the updated parameter as bf16 operand planes (same element
  * order), which fuses the re-pack of packed-layout weights into the optimiser step. */
-int pg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+int pg_adam_step(float* p, const void* g, int g_dtype /* PG_DT_F32 | PG_DT_BF16 */, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                  float eps, int step, float grad_scale, uint16_t* w_hi, uint16_t* w_lo, pg_stream stream);
 
 #ifdef __cplusplus

@@ -243,3 +243,28 @@ def test_optimizer_state_round_trip_resumes_identically(tmp_path):
     step2.load_state_dict(torch.load(str(tmp_path / "opt")))
     b = [float(step2(lm, ph)[0]) for _ in range(3)]
     assert a == b
+
+
+def test_bf16_gradient_path_tracks_the_fp32_one():
+    """grad_dtype="bf16" (the data-parallel default: wgrad writes bf16, NCCL would reduce bf16, Adam reads bf16)
+    against fp32 gradients from the same start: same loss trajectory to bf16 rounding of the gradients."""
+    import copy
+    import model
+    from phasegen.train import TrainStep
+    C, T, B = 128, 32, 4
+    torch.manual_seed(23)
+    lm = torch.rand(B, T, C, device="cuda") * 3
+    ph = (torch.rand(B, T, C, device="cuda") - 0.5) * 6
+    net_a = model.UNetModel(C, 2 * C).cuda()
+    net_b = model.UNetModel(C, 2 * C).cuda()
+    net_b.model.load_state_dict(copy.deepcopy(net_a.model.state_dict()))
+    sa = TrainStep(net_a, B, T, "cuda", precision="bf16x3", grad_dtype="fp32")
+    sb = TrainStep(net_b, B, T, "cuda", precision="bf16x3", grad_dtype="bf16")
+    assert sb.ex.dw_up[0].dtype == torch.bfloat16 and sa.ex.dw_up[0].dtype == torch.float32
+    la = [float(sa(lm, ph)[0]) for _ in range(6)]
+    lb = [float(sb(lm, ph)[0]) for _ in range(6)]
+    assert la[0] == lb[0]                                        # identical forward before the first update
+    assert la[-1] < la[0] and lb[-1] < lb[0]
+    assert max(abs(a - b) / a for a, b in zip(la, lb)) < 2e-3
+    wa = net_a.model.model[0].weight.detach().float(); wb = net_b.model.model[0].weight.detach().float()
+    assert float((wa - wb).norm() / wa.norm()) < 2e-3

@@ -219,14 +219,23 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
             float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale,
-            uint16_t* __restrict__ w_hi, uint16_t* __restrict__ w_lo) {
+            uint16_t* __restrict__ w_hi, uint16_t* __restrict__ w_lo, int g_bf16) {
+    const __nv_bfloat16* g16 = reinterpret_cast<const __nv_bfloat16*>(g);
     const float lr_bc1 = lr / bc1, bc2_sqrt_inv = 1.f / bc2_sqrt;
     const size_t n4 = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                         reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
                       ((reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo)) & 7) == 0 ? n / 4 : 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         float4 pi = reinterpret_cast<float4*>(p)[i];
-        const float4 gi = __ldg(reinterpret_cast<const float4*>(g) + i);
+        float4 gi;
+        if (g_bf16) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(g16) + i);
+            const float2 lo2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+            const float2 hi2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+            gi = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+        } else {
+            gi = __ldg(reinterpret_cast<const float4*>(g) + i);
+        }
         float4 mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i];
         adam_one(pi.x, gi.x, mi.x, vi.x, lr_bc1, b1, b2, eps, bc2_sqrt_inv, grad_scale);
         adam_one(pi.y, gi.y, mi.y, vi.y, lr_bc1, b1, b2, eps, bc2_sqrt_inv, grad_scale);
@@ -245,7 +254,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     }
     for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float pi = p[i], mi = m[i], vi = v[i];
-        adam_one(pi, g[i], mi, vi, lr_bc1, b1, b2, eps, bc2_sqrt_inv, grad_scale);
+        adam_one(pi, g_bf16 ? __bfloat162float(g16[i]) : g[i], mi, vi, lr_bc1, b1, b2, eps, bc2_sqrt_inv, grad_scale);
         p[i] = pi; m[i] = mi; v[i] = vi;
         if (w_hi) {
             uint16_t h, l;
@@ -322,12 +331,13 @@ extern "C" int pg_unpack_grad(const float* packed, int kind, int C_in, int C_out
     return check_launch("unpack_grad_kernel");
 }
 
-extern "C" int pg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+extern "C" int pg_adam_step(float* p, const void* g, int g_dtype, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                             float eps, int step, float grad_scale, uint16_t* w_hi, uint16_t* w_lo, pg_stream stream) {
+    PG_REQUIRE(g_dtype == PG_DT_F32 || g_dtype == PG_DT_BF16, "pg_adam_step: gradient dtype must be PG_DT_F32 or PG_DT_BF16");
     PG_REQUIRE(p && g && m && v && n > 0 && step >= 1, "pg_adam_step: bad arguments");
     const float bc1 = 1.f - powf(beta1, (float)step);
     const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
     int gx = (int)((n / 4 + 255) / 256); if (gx > 148 * 16) gx = 148 * 16; if (gx < 1) gx = 1;
-    adam_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale, w_hi, w_lo);
+    adam_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, static_cast<const float*>(g), m, v, (size_t)n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale, w_hi, w_lo, g_dtype == PG_DT_BF16 ? 1 : 0);
     return check_launch("adam_kernel");
 }

@@ -20,6 +20,7 @@ namespace pg {
 struct WgradParams {
     ConvPlan plan;
     float* dw;
+    int dw_bf16;        // dw is a bf16 buffer (same packed order): the gradient leaves for a bf16 all-reduce
     int nci;            // ci tile width (MMA N): 64 or 128
     int R, RB;          // K rows per stage of G, of the X strip (R + 8)
     int n_mchunks;
@@ -179,14 +180,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
             const int co = (PAIR ? w.co_tile * 2 + rank : w.co_tile) * 128 + q * 32 + lane;
             for (int j = 0; j < grp.n_taps; ++j) {
                 const ConvTap tp = pl.taps[w.phase][grp.first_tap + j];
-                float* dst = prm.dw + ((size_t)tp.w_idx * pl.C_out + co) * pl.C_in + (size_t)w.ci_tile * prm.nci;
+                const size_t off = ((size_t)tp.w_idx * pl.C_out + co) * pl.C_in + (size_t)w.ci_tile * prm.nci;
+                float* dst = prm.dw + off;
+                __nv_bfloat16* dst16 = reinterpret_cast<__nv_bfloat16*>(prm.dw) + off;
                 const uint32_t taddr = tmem_base + j * prm.nci + ((uint32_t)(q * 32) << 16);
                 for (int c0 = 0; c0 < prm.nci; c0 += 16) {
                     float v[16];
                     tmem_ld16(taddr + c0, v);
+                    if (prm.dw_bf16) {
+                        __align__(16) __nv_bfloat162 h[8];
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                        *reinterpret_cast<uint4*>(dst16 + c0) = *reinterpret_cast<uint4*>(&h[0]);
+                        *reinterpret_cast<uint4*>(dst16 + c0 + 8) = *reinterpret_cast<uint4*>(&h[4]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    }
                 }
             }
             tc_fence_before();
@@ -202,9 +213,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
 }  // namespace pg
 
 extern "C" int pg_wgrad_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* g_hi,
-                           const uint16_t* g_lo, int g_rows, float* dw_packed, pg_stream stream) {
+                           const uint16_t* g_lo, int g_rows, void* dw_packed, int dw_dtype, pg_stream stream) {
     using namespace pg;
     PG_REQUIRE(d && x_hi && g_hi && dw_packed, "pg_wgrad_tc: null pointer");
+    PG_REQUIRE(dw_dtype == PG_DT_F32 || dw_dtype == PG_DT_BF16, "pg_wgrad_tc: gradient dtype must be PG_DT_F32 or PG_DT_BF16");
     PG_REQUIRE(d->precision == PG_PREC_BF16X3 || d->precision == PG_PREC_BF16, "pg_wgrad_tc: precision must be BF16X3 or BF16");
     const bool three = d->precision == PG_PREC_BF16X3;
     PG_REQUIRE(!three || (x_lo && g_lo), "pg_wgrad_tc: lo planes required for BF16X3");
@@ -218,7 +230,8 @@ extern "C" int pg_wgrad_tc(const pg_conv_desc* d, const uint16_t* x_hi, const ui
     const ConvPlan& pl = prm.plan;
     int sm_count, max_smem;
     device_limits(&sm_count, &max_smem);
-    prm.dw = dw_packed;
+    prm.dw = static_cast<float*>(dw_packed);
+    prm.dw_bf16 = dw_dtype == PG_DT_BF16 ? 1 : 0;
     prm.n_terms = three ? 3 : 1;
     prm.nci = d->C_in % 128 == 0 ? 128 : 64;
     {

@@ -183,17 +183,17 @@ class UNetModel(nn.Module):
         self._ensure_packed(ex)
         return ex
 
-    def train_executor(self, B, T, device, precision=None):
+    def train_executor(self, B, T, device, precision=None, grad_dtype=torch.float32):
         """Executor that keeps what the backward pass needs (batch statistics, raw conv outputs)."""
         from phasegen.train import TrainExecutor
         levels = self._levels()
         prec = precision or (self.train_precision if self.train_precision != "auto" else self._resolve_precision(levels))
         if prec.startswith("f16"):
             prec = "bf16x3"     # the fp16 operand modes are inference-only; autograd runs the bf16 fp32-class form
-        key = ("train", B, T, str(device), prec)
+        key = ("train", B, T, str(device), prec, grad_dtype)
         ex = self._exec.get(key)
         if ex is None:
-            ex = TrainExecutor(levels, B, T, device, prec)
+            ex = TrainExecutor(levels, B, T, device, prec, grad_dtype=grad_dtype)
             self._exec[key] = ex
             self._packed.pop(id(ex), None)
         self._ensure_packed(ex)

@@ -59,10 +59,10 @@ _SIGNATURES = {
     "pg_transpose": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _L, _I, _I, _P]),
     "pg_phase_loss": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _I, _P, _P]),
     "pg_bn_bwd": (_I, [_P, _I, _I, _I, _P, _P, _F, C.POINTER(GradSrc), C.POINTER(GradSrc), _P, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
-    "pg_wgrad_tc": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _I, _P, _P]),
+    "pg_wgrad_tc": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _I, _P, _I, _P]),
     "pg_wgrad_simt": (_I, [C.POINTER(ConvDesc), _P, _P, _I, _P, _P]),
     "pg_unpack_grad": (_I, [_P, _I, _I, _I, _I, _P, _P]),
-    "pg_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P, _P, _P]),
+    "pg_adam_step": (_I, [_P, _P, _I, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P, _P, _P]),
     "pg_cast_split": (_I, [_P, _L, _P, _P, _I, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)

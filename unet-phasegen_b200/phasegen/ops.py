@@ -224,7 +224,8 @@ def bn_bwd(z, B, L, Cn, scale_shift, mean_var, eps, g0, g1, partial, coef, dgamm
 
 
 def wgrad_tc(desc, x_hi, x_lo, g_hi, g_lo, g_rows, dw_packed):
-    _lib.call("pg_wgrad_tc", C.byref(desc), _ptr(x_hi), _ptr(x_lo), _ptr(g_hi), _ptr(g_lo), g_rows, _ptr(dw_packed), _stream())
+    dt = PG_DT_BF16 if dw_packed.dtype == torch.bfloat16 else PG_DT_F32
+    _lib.call("pg_wgrad_tc", C.byref(desc), _ptr(x_hi), _ptr(x_lo), _ptr(g_hi), _ptr(g_lo), g_rows, _ptr(dw_packed), dt, _stream())
 
 
 def wgrad_simt(desc, x, g, g_rows, dw_packed):
@@ -237,7 +238,8 @@ def unpack_grad(packed, kind, out):
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0, w_hi=None, w_lo=None):
-    _lib.call("pg_adam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps, step, grad_scale,
+    gdt = PG_DT_BF16 if g.dtype == torch.bfloat16 else PG_DT_F32
+    _lib.call("pg_adam_step", _ptr(p), _ptr(g), gdt, _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps, step, grad_scale,
               _ptr(w_hi), _ptr(w_lo), _stream())
 
 
