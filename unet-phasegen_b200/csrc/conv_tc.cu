@@ -453,6 +453,10 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     }
     const int n_tiles = (pair ? pl.n_cotiles / 2 : pl.n_cotiles) * pl.OS * ((pl.B + pl.nb - 1) / pl.nb) * pl.n_ntiles;
     int units = pair ? g_sm_count / 2 : g_sm_count;           // persistent CTAs (or CTA pairs: one per TPC)
+    if (const char* e = getenv("PG_TC_MAX_CTAS")) {           // experiment hook: leave SMs free (e.g. for NCCL)
+        const int cap = atoi(e);
+        if (cap > 0 && units > (pair ? cap / 2 : cap)) units = pair ? cap / 2 : cap;
+    }
     if (d->tc_max_ctas > 0 && units > (pair ? (d->tc_max_ctas + 1) / 2 : d->tc_max_ctas)) units = pair ? (d->tc_max_ctas + 1) / 2 : d->tc_max_ctas;
     if (units > n_tiles) units = n_tiles;
     cudaLaunchConfig_t cfg = {};

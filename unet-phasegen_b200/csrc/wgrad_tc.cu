@@ -285,6 +285,10 @@ extern "C" int pg_wgrad_tc(const pg_conv_desc* d, const uint16_t* x_hi, const ui
     }
     const int n_items = (pair ? pl.n_cotiles / 2 : pl.n_cotiles) * (pl.C_in / prm.nci) * (pl.n_groups[0] + pl.n_groups[1]);
     int units = pair ? sm_count / 2 : sm_count;
+    if (const char* e = getenv("PG_TC_MAX_CTAS")) {           // experiment hook: leave SMs free (e.g. for NCCL)
+        const int cap = atoi(e);
+        if (cap > 0 && units > (pair ? cap / 2 : cap)) units = pair ? cap / 2 : cap;
+    }
     if (d->tc_max_ctas > 0 && units > (pair ? (d->tc_max_ctas + 1) / 2 : d->tc_max_ctas)) units = pair ? (d->tc_max_ctas + 1) / 2 : d->tc_max_ctas;
     if (units > n_items) units = n_items;
     cudaLaunchConfig_t cfg = {};

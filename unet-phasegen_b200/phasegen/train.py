@@ -69,6 +69,24 @@ class TrainExecutor(UNetExecutor):
         self.coef = torch.empty(cmax, 2, **f32)
         self.loss_partial = torch.empty(1024, 3, device=dev, dtype=torch.float64)
         self.loss3 = torch.zeros(4, **f32)
+        self._wg_desc = {}
+
+    def reserve_sms_in_backward(self, n_ctas):
+        """Cap the persistent grids of the backward tensor-core kernels (dgrad, wgrad) at `n_ctas` CTAs so that
+        `148 - n_ctas` SMs stay free for the NCCL all-reduce kernels that run beside them in data-parallel
+        training.  Without it an all-reduce that grabbed SMs at a kernel boundary delays the CTAs of the next
+        persistent kernel, whose statically assigned tiles then finish late (measured at 8 GPUs: 13.85 -> 13.42
+        ms per step with 16 SMs reserved; 32 reserved is too many: 16.7 ms)."""
+        from ._lib import ConvDesc
+        for lst in (self.dgrad_dn, self.dgrad_up):
+            for d in lst:
+                if d is not None:
+                    d.tc_max_ctas = int(n_ctas)
+        self._wg_desc = {}
+        for d in list(self.dn_desc) + list(self.up_desc):
+            c = ConvDesc.from_buffer_copy(d)
+            c.tc_max_ctas = int(n_ctas)
+            self._wg_desc[id(d)] = c
 
     def pack_weights(self, down_w, up_w):
         """Forward operands; the SIMT path additionally packs each weight with the other `kind` for the
@@ -99,7 +117,7 @@ class TrainExecutor(UNetExecutor):
         if self.prec == PG_PREC_FP32_SIMT:
             ops.wgrad_simt(desc, x_operand.hi, dz.hi, dz.rows, dw)
         else:
-            ops.wgrad_tc(desc, x_operand.hi, x_operand.lo, dz.hi, dz.lo, dz.rows, dw)
+            ops.wgrad_tc(self._wg_desc.get(id(desc), desc), x_operand.hi, x_operand.lo, dz.hi, dz.lo, dz.rows, dw)
         if self.grad_hook is not None:
             self.grad_hook(dw)                  # e.g. start this layer's all-reduce while the rest of backward runs
         if mirror is not None:
@@ -153,9 +171,10 @@ class TrainStep:
     def __init__(self, net, B, T, device, precision="bf16", lr=1e-3, betas=(0.9, 0.999), eps=1e-8, mag_weight=0.2,
                  grad_dtype=None):
         """grad_dtype: dtype of the weight gradients the wgrad kernel writes, NCCL reduces and Adam reads:
-        "fp32" (default on one GPU: what autograd would give) or "bf16" (default in data-parallel runs on the
-        tensor-core precisions: half the all-reduce volume -- 1.22 GB instead of 2.45 GB for UNetModel(1024, 2048)
-        -- and 2 B/parameter less HBM traffic in wgrad and in Adam; moments and master weights stay fp32)."""
+        "fp32" (default for the fp32-class precisions: what autograd would give) or "bf16" (default for
+        precision="bf16", on any number of GPUs: half the all-reduce volume -- 1.22 GB instead of 2.45 GB for
+        UNetModel(1024, 2048) -- and 2 B/parameter less HBM traffic in wgrad and in Adam; moments and master
+        weights stay fp32)."""
         import torch.distributed as dist
         self.net, self.lr, self.betas, self.eps, self.mag_weight = net, lr, betas, eps, mag_weight
         blocks = net._blocks()
@@ -165,9 +184,11 @@ class TrainStep:
                     conv.weight.data = ops.to_packed_storage(conv.weight.data, kind)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         if grad_dtype is None:
-            grad_dtype = "bf16" if (self.world > 1 and precision in ("bf16", "bf16x3")) else "fp32"
+            grad_dtype = "bf16" if precision == "bf16" else "fp32"
         self.grad_dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[grad_dtype]
         self.ex = net.train_executor(B, T, device, precision, grad_dtype=self.grad_dtype)
+        if self.world > 1 and self.ex.prec != PG_PREC_FP32_SIMT:
+            self.ex.reserve_sms_in_backward(132)
         self.t = 0
         ex = self.ex
         tc = ex.prec != PG_PREC_FP32_SIMT
