@@ -307,3 +307,38 @@ class TrainStep:
                 dst.copy_(src)
         self.t = int(sd["step"])
         self.lr, self.betas, self.eps = float(sd["lr"]), tuple(sd["betas"]), float(sd["eps"])
+
+
+class HostBatchFeeder:
+    """Uploads (log-magnitude, phase) batches from pinned host memory on a copy stream into two persistent device
+    slots, so the H2D copy of batch i+1 overlaps the training step of batch i (train.py:42,49-50,57 upload
+    synchronously every step).  Usage per step: ``lm, ph = feeder.upload(host_lm, host_ph)`` (returns at once,
+    the compute stream is made to wait for the copy), ``loss = step(lm, ph)``, ``feeder.done()``."""
+
+    def __init__(self, shape, device):
+        self.dev = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.slots = [(torch.empty(shape, device=self.dev), torch.empty(shape, device=self.dev)) for _ in range(2)]
+        self.free = [None, None]                  # event: the step that read this slot has finished
+        self.i = 0
+
+    def upload(self, host_lm, host_ph):
+        k = self.i & 1
+        lm, ph = self.slots[k]
+        cur = torch.cuda.current_stream(self.dev)
+        if self.free[k] is not None:
+            self.stream.wait_event(self.free[k])
+        with torch.cuda.stream(self.stream):
+            lm.copy_(host_lm, non_blocking=True)
+            ph.copy_(host_ph, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        cur.wait_event(ev)
+        self._k = k
+        return lm, ph
+
+    def done(self):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self.free[self._k] = ev
+        self.i += 1
