@@ -117,6 +117,10 @@ int pg_cast_split(const float* src, int64_t n, uint16_t* hi, uint16_t* lo, int f
 int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo,
                const uint16_t* w_hi, const uint16_t* w_lo, float* y, float* stats, pg_stream stream);
 int pg_conv_stat_parts(const pg_conv_desc* d);
+/* Tiling plan of pg_conv_tc for a layer, host-only: out[16] = {n_tile, n_ntiles, clips per tile, strip rows, CTA pair,
+ * merged clips, MMA groups per weight tile, TMEM accumulator stages, C_in/64, C_out/128, output phases, input
+ * parities, taps of phase 0, of phase 1, tap groups of phase 0, of phase 1}. */
+int pg_conv_tc_plan(const pg_conv_desc* d, int* out, int n_out);
 /* exact fp32 on CUDA cores; x fp32 [B][in_rows][in_ld], w_simt from pg_pack_weight. */
 int pg_conv_simt(const pg_conv_desc* d, const float* x, const float* w_simt, float* y, pg_stream stream);
 int pg_channel_stats(const float* y, int B, int L, int C, int rows, int ld, float* stats, pg_stream stream);

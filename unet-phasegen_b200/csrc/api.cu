@@ -26,7 +26,7 @@ int check_launch(const char* what) {
 }  // namespace pg
 
 extern "C" const char* pg_last_error(void) { return pg::g_err; }
-extern "C" int pg_abi_version(void) { return 1; }
+extern "C" int pg_abi_version(void) { return 2; }
 
 extern "C" int pg_check_device(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0, n = 0;
@@ -54,4 +54,17 @@ extern "C" int pg_conv_stat_parts(const pg_conv_desc* d) {
     int rc = pg::conv_plan_build(d, &pl);
     if (rc != PG_OK) return rc;
     return pl.OS * pl.n_ntiles;
+}
+
+// Host-side view of the tensor-core tiling decisions for a layer (no GPU needed): lets the tests pin the plan
+// (tile width, clips per tile, CTA pairs, merged clips, accumulator stages) for the BASELINE shapes.
+extern "C" int pg_conv_tc_plan(const pg_conv_desc* d, int* out, int n_out) {
+    PG_REQUIRE(d && out && n_out >= 16, "pg_conv_tc_plan: need a descriptor and room for 16 ints");
+    pg::ConvPlan p;
+    int rc = pg::conv_plan_build(d, &p);
+    if (rc != PG_OK) return rc;
+    const int v[16] = {p.n_tile, p.n_ntiles, p.nb, p.strip_rows, p.pair, p.merged, p.mgroups, p.acc_stages,
+                       p.n_chunks, p.n_cotiles, p.OS, p.IS, p.n_taps[0], p.n_taps[1], p.n_groups[0], p.n_groups[1]};
+    for (int i = 0; i < 16; ++i) out[i] = v[i];
+    return PG_OK;
 }

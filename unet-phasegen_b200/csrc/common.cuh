@@ -10,6 +10,9 @@
 namespace pg {
 
 void set_error(const char* fmt, ...);
+// cudaFuncSetAttribute is per device: opt-in bookkeeping is keyed by the current device ordinal
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() { int dev = 0; cudaGetDevice(&dev); return dev >= 0 && dev < kMaxDevices ? dev : 0; }
 int check_launch(const char* what);
 
 #define PG_REQUIRE(cond, ...)                 \

@@ -433,7 +433,8 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     }
     const bool pair = pl.pair != 0;
     {
-        static size_t configured[2] = {0, 0};
+        static size_t configured_dev[kMaxDevices][2] = {};
+        size_t* configured = configured_dev[current_device_slot()];
         if (smem_bytes > configured[pair]) {
             cudaError_t e = pair ? cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)
                                  : cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);

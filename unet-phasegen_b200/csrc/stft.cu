@@ -332,7 +332,8 @@ static int launch_stft(const float* wave, int B, int N, int T, const float* tw, 
     const bool fast = mode == PG_STFT_LOGMAG && a && !bq && hi && lo;
     auto k = !fast ? stft_kernel<NC, 0> : fmt == PG_FMT_F16 ? stft_kernel<NC, 2> : stft_kernel<NC, 1>;
     const size_t sm = Cfg::smem_stft();
-    static bool configured = false;
+    static bool configured_dev[kMaxDevices] = {};
+    bool& configured = configured_dev[current_device_slot()];
     if (!configured) {
         cudaFuncSetAttribute(stft_kernel<NC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         cudaFuncSetAttribute(stft_kernel<NC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -351,7 +352,8 @@ static int launch_istft(const float* a, const float* bq, int mode, int B, int T,
     using Cfg = FrameCfg<NC>;
     auto k = (mode == PG_SPEC_POLAR_LOG && bq) ? istft_kernel<NC, true> : istft_kernel<NC, false>;
     const size_t sm = Cfg::smem_istft();
-    static bool configured = false;
+    static bool configured_dev[kMaxDevices] = {};
+    bool& configured = configured_dev[current_device_slot()];
     if (!configured) {
         cudaFuncSetAttribute(istft_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         cudaFuncSetAttribute(istft_kernel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

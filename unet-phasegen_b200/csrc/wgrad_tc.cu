@@ -276,7 +276,8 @@ extern "C" int pg_wgrad_tc(const pg_conv_desc* d, const uint16_t* x_hi, const ui
         if ((rc = encode_bf16_map(&mx_lo, three ? x_lo : x_hi, 4, dims, str, box, "x_lo")) != PG_OK) return rc;
     }
     const bool pair = prm.pair != 0;
-    static size_t configured[2] = {0, 0};
+    static size_t configured_dev[kMaxDevices][2] = {};
+    size_t* configured = configured_dev[current_device_slot()];
     if (smem_bytes > configured[pair]) {
         cudaError_t e = pair ? cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)
                              : cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);

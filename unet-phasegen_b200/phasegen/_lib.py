@@ -52,6 +52,7 @@ _SIGNATURES = {
     "pg_pack_weight": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "pg_conv_tc": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "pg_conv_stat_parts": (_I, [C.POINTER(ConvDesc)]),
+    "pg_conv_tc_plan": (_I, [C.POINTER(ConvDesc), C.POINTER(_I), _I]),
     "pg_conv_simt": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P]),
     "pg_channel_stats": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "pg_bn_finalize": (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _P, _P, _P]),
