@@ -172,7 +172,9 @@ static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
             const long slot_bytes = (long)planes_b * (2 * best_nb / (p->pair ? 2 : 1)) * strip_full * 128;   // per CTA, one strip slot
             const char* fr = getenv("PG_TC_MG_FRAC");           // experiment hook: fraction of the grid two-group tiles must fill
             const double need = (fr ? atof(fr) : 0.8) * units;    // 0.8: measured optimum (profiles/r01_conv_mgroups_ab.log)
-            if (2 * best_nb <= d->B && 2 * best_nb * strip_full <= 512 && (double)tiles2 >= need && 2 * slot_bytes <= 120 * 1024 &&
+            // (only where the weight stream is the bound: with three products per MAC the pipe is, and the lost
+            //  epilogue overlap costs 3 %: profiles/r01_conv_mgroups_ab.log)
+            if (weight_bound && 2 * best_nb <= d->B && 2 * best_nb * strip_full <= 512 && (double)tiles2 >= need && 2 * slot_bytes <= 120 * 1024 &&
                 !(g2 && atoi(g2) == 1)) {
                 p->mgroups = 2; p->nb = 2 * best_nb;
             }

@@ -223,7 +223,12 @@ extern "C" int pg_wgrad_tc(const pg_conv_desc* d, const uint16_t* x_hi, const ui
     PG_REQUIRE(d->C_in % 64 == 0 && d->C_out % 128 == 0 && d->in_ld % 8 == 0, "pg_wgrad_tc: needs C_in %% 64 == 0 and C_out %% 128 == 0");
     WgradParams prm;
     pg_conv_desc dd = *d;
-    dd.taps_per_group = 4;            // 4 accumulators of <= 128 columns fill TMEM
+    // TMEM holds 512 accumulator columns: 4 taps x 128 input channels, or (wide) 2 taps x 256 input channels.
+    // The wide form reads 12 KB of shared-memory operands per 128 math cycles instead of 8 KB per 64.
+    // Measured (train shapes, bf16): 12.03 -> 11.01 ms per step with the wide form.
+    bool wide = d->C_in % 256 == 0;
+    if (const char* e = getenv("PG_WG_NCI")) wide = wide && atoi(e) == 256;                 // A/B hook: PG_WG_NCI=128
+    dd.taps_per_group = wide ? 2 : 4;
     dd.max_clips_per_tile = 1;
     int rc = conv_plan_build(&dd, &prm.plan);
     if (rc != PG_OK) return rc;
@@ -233,7 +238,7 @@ extern "C" int pg_wgrad_tc(const pg_conv_desc* d, const uint16_t* x_hi, const ui
     prm.dw = static_cast<float*>(dw_packed);
     prm.dw_bf16 = dw_dtype == PG_DT_BF16 ? 1 : 0;
     prm.n_terms = three ? 3 : 1;
-    prm.nci = d->C_in % 128 == 0 ? 128 : 64;
+    prm.nci = wide ? 256 : d->C_in % 128 == 0 ? 128 : 64;
     {
         int want = d->tc_cta_pair;
         if (const char* e = getenv("PG_WG_PAIR")) want = atoi(e);   // A/B hook: 1 = single CTAs
