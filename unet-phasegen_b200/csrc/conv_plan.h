@@ -31,7 +31,7 @@ struct ConvPlan {
     int acc_stages;             // TMEM accumulator stages: 2 (nb*n_tile <= 256, epilogue overlaps MMA) or 1 (up to 512 columns)
     int pair;                   // tensor-core path: tiles are 256 channels wide, owned by a CTA pair (cta_group::2); strip_rows
                                 // is then the half strip (n_tile/2 + largest shift) each CTA of the pair loads
-    int mgroups;                // merged tiles: MMAs per weight tile (1 or 2); nb = mgroups * clips per MMA
+    int mgroups;                // merged tiles: MMAs per weight tile (1..4); nb = mgroups * clips per MMA
     int merged;                 // tensor-core path, short time axes: the nb/mgroups clips of a group are ONE MMA of N = (nb/mgroups)*strip_rows
                                 // (accumulator column pitch strip_rows per clip, the strip_rows - n_tile columns between clips
                                 // are junk); strip_rows is the full strip, a CTA pair splits the tile by clips
@@ -163,20 +163,23 @@ static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
                 if (best < 0 || cost <= best) { best = cost; best_nb = nb; }
             }
             p->merged = 1; p->nb = best_nb; p->strip_rows = strip_full;
-            // Two MMAs (2 x up to 256 accumulator columns, one TMEM stage) per weight tile while that still leaves
+            // Several MMAs (up to 512 accumulator columns in all, one TMEM stage) per weight tile while that still leaves
             // a tile for >= 80 % of the CTA pairs: the weight stream from L2 -- the bound of these layers, whose
             // weights are read once per tile -- halves.
-            const long tiles2 = (long)slabs * ((d->B + 2 * best_nb - 1) / (2 * best_nb));
-            const char* g2 = getenv("PG_TC_MGROUPS");
+            const char* g2 = getenv("PG_TC_MGROUPS");           // experiment hook: cap the number of groups
+            const int g_cap = g2 ? atoi(g2) : 2;                // 3 groups measured worse (u1 train shape: 1.92 vs 1.42 ms: the tile count drops to 1.3 waves)
             const int planes_b = (d->precision == PG_PREC_BF16X3 || d->precision == PG_PREC_F16X3 || d->precision == PG_PREC_F16X2) ? 2 : 1;
-            const long slot_bytes = (long)planes_b * (2 * best_nb / (p->pair ? 2 : 1)) * strip_full * 128;   // per CTA, one strip slot
-            const char* fr = getenv("PG_TC_MG_FRAC");           // experiment hook: fraction of the grid two-group tiles must fill
+            const char* fr = getenv("PG_TC_MG_FRAC");           // experiment hook: fraction of the grid multi-group tiles must fill
             const double need = (fr ? atof(fr) : 0.8) * units;    // 0.8: measured optimum (profiles/r01_conv_mgroups_ab.log)
             // (only where the weight stream is the bound: with three products per MAC the pipe is, and the lost
             //  epilogue overlap costs 3 %: profiles/r01_conv_mgroups_ab.log)
-            if (weight_bound && 2 * best_nb <= d->B && 2 * best_nb * strip_full <= 512 && (double)tiles2 >= need && 2 * slot_bytes <= 120 * 1024 &&
-                !(g2 && atoi(g2) == 1)) {
-                p->mgroups = 2; p->nb = 2 * best_nb;
+            for (int g = 4; g >= 2 && weight_bound; --g) {
+                if (g > g_cap || g * best_nb > d->B || g * best_nb * strip_full > 512) continue;
+                const long tiles_g = (long)slabs * ((d->B + g * best_nb - 1) / (g * best_nb));
+                const long slot_bytes = (long)planes_b * (g * best_nb / (p->pair ? 2 : 1)) * strip_full * 128;   // per CTA, one strip slot
+                if ((double)tiles_g < need || 2 * slot_bytes > 120 * 1024) continue;
+                p->mgroups = g; p->nb = g * best_nb;
+                break;
             }
         }
     }

@@ -244,7 +244,7 @@ extern "C" int pg_wgrad_tc(const pg_conv_desc* d, const uint16_t* x_hi, const ui
         if (const char* e = getenv("PG_WG_PAIR")) want = atoi(e);   // A/B hook: 1 = single CTAs
         // opt-in only (tc_cta_pair = 2): measured neutral-to-slightly-slower than single CTAs at the train shapes
         // (12.46 vs 12.29 ms per step) -- this kernel is not bound by its shared-memory operand reads
-        prm.pair = (want == 2 && prm.nci == 128 && d->C_out % 256 == 0) ? 1 : 0;
+        prm.pair = (want == 2 && prm.nci >= 128 && d->C_out % 256 == 0) ? 1 : 0;
     }
     const int l_max = (pl.L_out + pl.OS - 1) / pl.OS;
     const int r_cap = three ? 64 : 128;
