@@ -459,7 +459,7 @@ def main():
         del pipe3
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:     # reported at N = 1 only
         dt, done = cpu_reference_step(16, time_budget_s=12.0)
         cpu = {"value": clip_s * done / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                "sample": f"{done} clips of the same workload, batch-1 per clip (demo.py loop), numpy STFT/ISTFT + torch-CPU fp32 U-Net (oneDNN off)"}
