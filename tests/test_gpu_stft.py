@@ -172,3 +172,43 @@ def test_griffin_lim_matches_the_intended_algorithm():
     rb = rb.cpu().numpy()
     assert rel_l2(rb[0] / np.abs(rb[0]).max(), a) < 1e-5 and rel_l2(rb[1] / np.abs(rb[1]).max(), a2) < 1e-5
     assert abs(float(lb[1]) - l2) < 1e-4 * l2
+
+
+@pytest.mark.parametrize("n_fft,hop", [(1024, 256), (256, 64), (2048, 512)])
+def test_stft_ragged_lengths_and_unaligned_clips(n_fft, hop):
+    """Edge cases of the frame loader: an odd clip length (no float2 path, frame count 1 + N // hop with a
+    partial last hop), a batch whose base pointer is only 4-byte aligned, the shortest legal clip (N = n_fft/2 + 1:
+    every frame touches both reflections), and a frame count that is not a multiple of the frames per CTA."""
+    from phasegen import ops
+    rng = np.random.default_rng(n_fft)
+    for N in (n_fft // 2 + 1, 5 * hop + 37, 41 * hop + 1, 33 * hop):
+        w = rng.standard_normal((3, N)).astype(np.float32)
+        buf = torch.zeros(3 * N + 1, device="cuda")
+        buf[1:] = torch.from_numpy(w).reshape(-1).cuda()
+        for wave in (torch.from_numpy(w).cuda(), buf[1:].view(3, N)):          # aligned base, then base + 4 bytes
+            lm, ph = ops.stft(wave, n_fft, hop)
+            assert lm.shape == (3, 1 + N // hop, n_fft // 2)
+            for b in range(3):
+                S = stft_np.stft(w[b], n_fft, hop)[1:]
+                assert rel_l2(lm[b].cpu().numpy().T, np.log1p(np.abs(S))) < 1e-4, (N, b)
+                z = np.expm1(lm[b].cpu().numpy().T.astype(np.float64)) * np.exp(1j * ph[b].cpu().numpy().T.astype(np.float64))
+                assert np.linalg.norm(z - S) / np.linalg.norm(S) < 1e-4, (N, b)
+
+
+@pytest.mark.parametrize("n_fft,hop", [(1024, 256), (512, 128)])
+@pytest.mark.parametrize("T", [2, 3, 5, 86, 87, 171])
+def test_istft_run_boundaries(n_fft, hop, T):
+    """The sliding overlap-add at its seams: fewer frames than one iteration, and frame counts that end exactly on,
+    one past and one short of a CTA's run of 11 * 8 - 3 = 85 hop-blocks (two CTAs per clip, halo frames on both sides)."""
+    from phasegen import ops
+    C = n_fft // 2
+    rng = np.random.default_rng(T)
+    re = rng.standard_normal((2, T, C)).astype(np.float32)
+    im = rng.standard_normal((2, T, C)).astype(np.float32)
+    wv, peak = ops.istft(torch.from_numpy(re).cuda(), torch.from_numpy(im).cuda(), ops.PG_SPEC_CARTESIAN, n_fft, hop, normalize=False)
+    for b in range(2):
+        z = np.concatenate([np.zeros((1, T)), re[b].T.astype(np.float64) + 1j * im[b].T.astype(np.float64)])
+        ref = stft_np.istft(z, hop)
+        assert wv.shape[1] == ref.shape[0]
+        assert rel_l2(wv[b].cpu().numpy(), ref) < 2e-5
+        assert abs(float(peak[b]) - np.abs(ref).max()) < 1e-4 * np.abs(ref).max()
