@@ -264,8 +264,10 @@ MMA_NOTES = {"bf16x3": "the fp32-class mode issues 3 bf16 MMAs per algorithmic M
 
 
 PARITY_NOTES = {
-    "f16mix": "predicted phase rel-L2 vs float64 oracle 4.8e-4 at C=512 (bound 1e-3; tests/test_gpu_unet.py), STFT log-magnitude < 1e-4",
-    "bf16x3": "predicted phase rel-L2 vs float64 oracle 9e-5 at C=512 (bound 1e-3), STFT log-magnitude < 1e-4",
+    "f16mix": "full path at this exact shape vs the float64 oracle (tests/test_gpu_pipeline.py::test_shape_sweep_full_path_one_clip): "
+              "predicted phase rel-L2 5.1e-4 (bound 1e-3), waveform SNR within 0.1 dB, STFT log-magnitude < 1e-4",
+    "bf16x3": "full path at this exact shape vs the float64 oracle: predicted phase rel-L2 9.7e-5 (bound 1e-3), waveform SNR "
+              "within 0.1 dB, STFT log-magnitude < 1e-4",
     "f16x3": "predicted phase rel-L2 vs float64 oracle 1e-4 at C=512 (bound 1e-3)",
     "f16x2": "predicted phase rel-L2 vs float64 oracle 7e-4 at C=512 (bound 1e-3: no margin, not the default)",
     "bf16": "loose mode: predicted phase rel-L2 ~1e-2", "fp32_simt": "exact fp32 CUDA-core convolutions"}
