@@ -98,3 +98,24 @@ def test_synthetic_shapes():
     w = synth.synthetic_waves(2, 1000, seed=3)
     assert w.shape == (2, 1000) and float(w.abs().max()) <= 1.0
     assert torch.equal(w, synth.synthetic_waves(2, 1000, seed=3))
+
+
+def test_logger_drop_in_on_stock_tensorboard(tmp_path):
+    """logger.Logger (reference logger.py:6-49) without tensorboardX: scalars / audio / images are accepted and
+    write() exports log.json."""
+    import json
+    from collections import OrderedDict
+    import logger
+    lg = logger.Logger(str(tmp_path / "run"))
+    lg.log(1, OrderedDict([("MSE", 0.5), ("NOPMSE", np.float32(0.25))]))
+    lg.log(2, OrderedDict([("MSE", 0.4)]), text=True)
+    lg.log(2, OrderedDict([("wav", np.zeros(800, np.float32))]), log_type="audio", sr=8000)
+    lg.log(2, OrderedDict([("img", np.zeros((20, 30, 3), np.uint8))]), log_type="image")
+    with pytest.raises(ValueError):
+        lg.log(3, {}, log_type="video")
+    with pytest.raises(ValueError):
+        lg.log(3, {"a": np.zeros(4)}, log_type="audio")
+    lg.write(); lg.flush(); lg.close()
+    data = json.load(open(tmp_path / "run" / "log.json"))
+    key = [k for k in data if k.endswith("scalar/MSE")][0]
+    assert [row[1:] for row in data[key]] == [[1, 0.5], [2, 0.4]]

@@ -268,3 +268,24 @@ def test_bf16_gradient_path_tracks_the_fp32_one():
     assert max(abs(a - b) / a for a, b in zip(la, lb)) < 2e-3
     wa = net_a.model.model[0].weight.detach().float(); wb = net_b.model.model[0].weight.detach().float()
     assert float((wa - wb).norm() / wa.norm()) < 2e-3
+
+
+def test_async_checkpoint_equals_sync_checkpoint(tmp_path):
+    """UNetModel.save_async: same file content as save(), written while the GPU keeps working."""
+    import model
+    net = model.UNetModel(64, 128).cuda()
+    x = torch.randn(2, 64, 32, device="cuda")
+    net.forward(x)                                              # moves the running statistics
+    h = net.save_async(str(tmp_path / "a"))
+    net.forward(x)                                              # work queued behind the snapshot must not leak into it
+    net.save(str(tmp_path / "b_after"))
+    h.wait()
+    a = torch.load(str(tmp_path / "a"))
+    net2 = model.UNetModel(64, 128).cuda()
+    net2.load(str(tmp_path / "a"))
+    for k, v in net2.model.state_dict().items():
+        assert torch.equal(v.cpu(), a[k]), k
+    b = torch.load(str(tmp_path / "b_after"))
+    assert set(a) == set(b)
+    assert int(a["model.4.num_batches_tracked"]) + 1 == int(b["model.4.num_batches_tracked"])
+    assert torch.equal(a["model.0.weight"], b["model.0.weight"])

@@ -130,6 +130,15 @@ class _UNetFunction(torch.autograd.Function):
         return (None, None) + tuple(net._param_grads(ex))
 
 
+class _SaveHandle:
+    def __init__(self, thread):
+        self._t = thread
+
+    def wait(self):
+        if self._t is not None:
+            self._t.join()
+
+
 class UNetModel(nn.Module):
     # "auto" | "bf16x3" (fp32-class, 3 bf16 tensor-core products) | "f16x3" (same on fp16 planes) | "f16mix"
     # (f16x3 with the two-product form on d1/u1/u2) | "f16x2" | "bf16" | "fp32_simt"
@@ -295,6 +304,38 @@ class UNetModel(nn.Module):
 
     def save(self, path):
         torch.save({k: v.detach().cpu() for k, v in self.model.state_dict().items()}, path)
+
+    def save_async(self, path):
+        """`save` without stalling the training stream: the state dict is copied to
+        pinned host buffers on a side stream and written by a background thread; training continues as soon as the
+        copy has been ordered after the work already queued.  Returns a handle whose ``.wait()`` joins the writer.
+        The file is the same inner-block ``state_dict`` the reference writes (model.py:45-48)."""
+        import threading
+        sd = self.model.state_dict()
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            self.save(path)
+            return _SaveHandle(None)
+        cur = torch.cuda.current_stream(dev)
+        side = self.__dict__.setdefault("_save_stream", torch.cuda.Stream(device=dev))
+        side.wait_stream(cur)
+        host = {}
+        with torch.cuda.stream(side):
+            for k, v in sd.items():
+                src = v.detach()
+                buf = torch.empty(src.shape, dtype=src.dtype, device="cpu", pin_memory=True)
+                buf.copy_(src, non_blocking=True)          # a strided (packed-storage) source lands contiguous
+                src.record_stream(side)
+                host[k] = buf
+            done = torch.cuda.Event()
+            done.record(side)
+
+        def writer():
+            done.synchronize()
+            torch.save(host, path)
+        t = threading.Thread(target=writer, daemon=True)
+        t.start()
+        return _SaveHandle(t)
 
     def load(self, path):
         state_dict = torch.load(path, map_location="cpu")
