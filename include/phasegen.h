@@ -81,8 +81,10 @@ enum { PG_CONV = 0, PG_CONV_TRANSPOSE = 1 };
  *   BF16  : Whi*Xhi, bf16                              (~2^-8; the separately stated loose mode)
  *   F16X3 : same three products on fp16 planes          (~2^-22; operands must stay inside the fp16 range)
  *   F16X2 : Whi*Xhi + Whi*Xlo, fp16: activations exact to 2^-22, weights rounded to fp16 (2^-11, the
- *           rounding of a TF32 operand) -- the cost of ONE TF32 pass with half of its rounding error */
-enum { PG_PREC_FP32_SIMT = 0, PG_PREC_BF16X3 = 1, PG_PREC_BF16 = 2, PG_PREC_F16X3 = 3, PG_PREC_F16X2 = 4 };
+ *           rounding of a TF32 operand) -- the cost of ONE TF32 pass with half of its rounding error
+ *   F16   : Whi*Xhi, fp16: both operands rounded to 11 significant bits -- exactly the operand rounding of a
+ *           TF32 pass (10-bit mantissa), at twice its tensor rate */
+enum { PG_PREC_FP32_SIMT = 0, PG_PREC_BF16X3 = 1, PG_PREC_BF16 = 2, PG_PREC_F16X3 = 3, PG_PREC_F16X2 = 4, PG_PREC_F16 = 5 };
 enum { PG_DT_NONE = 0, PG_DT_F32 = 1, PG_DT_BF16_SPLIT = 2, PG_DT_BF16 = 3, PG_DT_F16_SPLIT = 4, PG_DT_F16 = 5 };
 enum { PG_FMT_BF16 = 0, PG_FMT_F16 = 1 };   /* 16-bit format of operand planes written by a kernel */
 

@@ -75,7 +75,7 @@ def test_long_form_windows_match_pipeline_and_seams_sum_to_one():
     assert float((single[0] - per_window[2]).abs().max()) < 1e-5 * float(per_window[2].abs().max()) + 1e-7
 
 
-@pytest.mark.parametrize("prec", ["bf16x3", "f16mix"])
+@pytest.mark.parametrize("prec", ["bf16x3", "f16mix", "f16mix1"])
 @pytest.mark.parametrize("n_fft,T", [(512, 1384), (1024, 696), (2048, 352)])
 def test_shape_sweep_full_path_one_clip(n_fft, T, prec):
     """Config 5 shapes (n_fft 512 / hop 128 / T 1384 and n_fft 2048 / hop 512 / T 352) through the

@@ -116,7 +116,7 @@ static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
     // full-width tiles (measured: 72 % pipe-active at N = 176, profiles/r01_conv_tc_ncu_full_v2.csv), so two
     // clips share every weight tile (2 x 176 accumulator columns, one TMEM stage); the three-product forms
     // are pipe/power-bound there and keep the double-buffered accumulator.
-    const bool weight_bound = d->precision == PG_PREC_F16X2 || d->precision == PG_PREC_BF16;
+    const bool weight_bound = d->precision == PG_PREC_F16X2 || d->precision == PG_PREC_BF16 || d->precision == PG_PREC_F16;
     if ((p->n_ntiles == 1 || weight_bound) && d->max_clips_per_tile != 1) {
         // Up to 512 accumulator columns (one TMEM stage) when the strips of that many clips still leave
         // room for the weight ring: the weight tile, the dominant L2->SM stream for short time axes, is

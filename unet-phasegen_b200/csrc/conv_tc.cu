@@ -378,7 +378,7 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
                           const uint16_t* w_lo, float* y, float* stats, pg_stream stream) {
     using namespace pg;
     PG_REQUIRE(d && x_hi && w_hi && y, "pg_conv_tc: null pointer");
-    PG_REQUIRE(d->precision >= PG_PREC_BF16X3 && d->precision <= PG_PREC_F16X2, "pg_conv_tc: precision must be BF16X3, BF16, F16X3 or F16X2");
+    PG_REQUIRE(d->precision >= PG_PREC_BF16X3 && d->precision <= PG_PREC_F16, "pg_conv_tc: precision must be BF16X3, BF16, F16X3, F16X2 or F16");
     const int n_terms = (d->precision == PG_PREC_BF16X3 || d->precision == PG_PREC_F16X3) ? 3 : d->precision == PG_PREC_F16X2 ? 2 : 1;
     const bool three = n_terms == 3;
     PG_REQUIRE(n_terms < 3 || w_lo, "pg_conv_tc: weight lo plane required for the three-product precisions");
@@ -395,7 +395,7 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     { int a_, b_; device_limits(&a_, &b_); }
     prm.y = y; prm.stats = reinterpret_cast<float4*>(stats);
     prm.n_terms = n_terms;
-    prm.f16 = (d->precision == PG_PREC_F16X3 || d->precision == PG_PREC_F16X2) ? 1 : 0;
+    prm.f16 = (d->precision == PG_PREC_F16X3 || d->precision == PG_PREC_F16X2 || d->precision == PG_PREC_F16) ? 1 : 0;
     prm.base_offset_mode = d->tc_base_offset_mode;
     prm.a_mn = d->weights_mn_major ? 1 : 0;
     const int nb_grp = pl.nb / pl.mgroups;

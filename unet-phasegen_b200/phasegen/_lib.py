@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "..", "csrc", "libphasegen.so")
 
 PG_CONV, PG_CONV_TRANSPOSE = 0, 1
-PG_PREC_FP32_SIMT, PG_PREC_BF16X3, PG_PREC_BF16, PG_PREC_F16X3, PG_PREC_F16X2 = 0, 1, 2, 3, 4
+PG_PREC_FP32_SIMT, PG_PREC_BF16X3, PG_PREC_BF16, PG_PREC_F16X3, PG_PREC_F16X2, PG_PREC_F16 = 0, 1, 2, 3, 4, 5
 PG_DT_NONE, PG_DT_F32, PG_DT_BF16_SPLIT, PG_DT_BF16, PG_DT_F16_SPLIT, PG_DT_F16 = 0, 1, 2, 3, 4, 5
 PG_FMT_BF16, PG_FMT_F16 = 0, 1
 PG_STFT_LOGMAG, PG_STFT_REIM, PG_STFT_PROJECT, PG_STFT_PAIRS = 0, 1, 2, 3
@@ -19,7 +19,7 @@ PG_SPEC_POLAR_LOG, PG_SPEC_CARTESIAN, PG_SPEC_POLAR_MAG = 0, 1, 2
 # "f16mix" is an executor-level name (phasegen/unet.py): fp16 planes everywhere, the three-product
 # form on the small layers and the two-product form (fp16-rounded weights) on the three largest.
 PRECISIONS = {"fp32_simt": PG_PREC_FP32_SIMT, "bf16x3": PG_PREC_BF16X3, "bf16": PG_PREC_BF16,
-              "f16x3": PG_PREC_F16X3, "f16x2": PG_PREC_F16X2}
+              "f16x3": PG_PREC_F16X3, "f16x2": PG_PREC_F16X2, "f16": PG_PREC_F16}
 
 
 class ConvDesc(C.Structure):

@@ -18,7 +18,7 @@ import torch
 
 from . import ops
 from ._lib import (PG_CONV, PG_CONV_TRANSPOSE, PG_DT_BF16, PG_DT_BF16_SPLIT, PG_DT_F16_SPLIT, PG_DT_F32, PG_PREC_BF16,
-                   PG_PREC_BF16X3, PG_PREC_F16X2, PG_PREC_F16X3, PG_PREC_FP32_SIMT, PRECISIONS)
+                   PG_PREC_BF16X3, PG_PREC_F16, PG_PREC_F16X2, PG_PREC_F16X3, PG_PREC_FP32_SIMT, PRECISIONS)
 
 BN_EPS_DEFAULT = 1e-5
 # Taps that share one TMA-loaded activation strip in the tensor-core kernel (1 = no strip reuse).
@@ -30,8 +30,12 @@ DEFAULT_TAPS_PER_GROUP = 16
 # exactly these three the predicted phase stays within ~5e-4 relative L2 of the float64 oracle
 # (bound: 1e-3), measured in tests/test_gpu_unet.py.
 F16MIX_FAST_LAYERS = ("d1", "u1", "u2")
+# precision="f16mix1": as f16mix, plus the LAST layer (u1, 36 % of the multiply-adds) with a single fp16 product:
+# both operands rounded to 11 significant bits = the operand rounding of a TF32 pass at twice its rate.  Its
+# rounding error is not amplified by any later layer; measured phase error in tests/test_gpu_pipeline.py.
+F16MIX1_SINGLE_LAYERS = ("u1",)
 _SPLIT_PRECS = (PG_PREC_BF16X3, PG_PREC_F16X3, PG_PREC_F16X2)
-_F16_PRECS = (PG_PREC_F16X3, PG_PREC_F16X2)
+_F16_PRECS = (PG_PREC_F16X3, PG_PREC_F16X2, PG_PREC_F16)
 DEFAULT_BASE_OFFSET_MODE = 0
 
 
@@ -96,11 +100,15 @@ class UNetExecutor:
     def __init__(self, levels, B, T, device, precision="bf16x3", per_clip=False, out_channels=None,
                  taps_per_group=None, base_offset_mode=None, keep_raw=False, fast_layers=None):
         self.levels, self.B, self.T, self.device = levels, B, T, torch.device(device)
+        single_layers = ()
+        if precision == "f16mix1":
+            precision, single_layers = "f16mix", F16MIX1_SINGLE_LAYERS
         if precision == "f16mix":
             precision, fast_layers = "f16x3", (F16MIX_FAST_LAYERS if fast_layers is None else fast_layers)
         self.prec = PRECISIONS[precision] if isinstance(precision, str) else precision
         # per-layer precision: the executor's, except that fp16 executors may run named layers two-product
         self.fast_layers = tuple(fast_layers or ()) if self.prec == PG_PREC_F16X3 else ()
+        self.single_layers = tuple(single_layers) if self.prec == PG_PREC_F16X3 else ()
         if self.prec != PG_PREC_FP32_SIMT and not tc_supported(levels):
             raise RuntimeError("phasegen: tensor-core path needs C_in % 64 == 0 and C_out % 128 == 0 in every "
                                "layer; use precision='fp32_simt' for this channel count")
@@ -168,6 +176,8 @@ class UNetExecutor:
 
     def layer_prec(self, side, level):
         """Precision of the down ("d") or up ("u") convolution of a level."""
+        if self.prec == PG_PREC_F16X3 and f"{side}{level + 1}" in self.single_layers:
+            return PG_PREC_F16
         if self.prec == PG_PREC_F16X3 and f"{side}{level + 1}" in self.fast_layers:
             return PG_PREC_F16X2
         return self.prec
