@@ -216,6 +216,7 @@ def run_train(args):
         loss_ev[k] = torch.cuda.Event(); loss_ev[k].record()
         e2e_i[0] += 1
 
+    e2e_chunks = pipe.suggest_chunks(B, N, dev) if args.e2e_chunks == 0 else args.e2e_chunks
     for _ in range(W):
         step_resident()
     sampler = ClockSampler(local)
@@ -288,7 +289,8 @@ def main():
                     help="inference default: f16mix (fp32-class, within the 1e-3 phase bound; the all-three-product bf16x3 "
                          "figure is reported beside it); training default: bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="sub-batches whose copies overlap GPU work in the e2e leg")
+    ap.add_argument("--e2e-chunks", type=int, default=0,
+                    help="sub-batches whose copies overlap GPU work in the e2e leg (0 = wave-aligned sizes from PhaseGenPipeline.suggest_chunks)")
     ap.add_argument("--workload", default="infer", choices=["infer", "train"],
                     help="infer = BASELINE config 2 (headline, default); train = config 3 (train.py step)")
     ap.add_argument("--train-batch", type=int, default=32)
@@ -355,8 +357,9 @@ def main():
 
     def step_e2e():
         # the public host-buffer call: pinned host wave in, pinned host wave out, copies inside
-        pipe.run_host(host_in, host_out, chunks=args.e2e_chunks)
+        pipe.run_host(host_in, host_out, chunks=e2e_chunks)
 
+    e2e_chunks = pipe.suggest_chunks(B, N, dev) if args.e2e_chunks == 0 else args.e2e_chunks
     for _ in range(W):
         step_resident()
     sampler = ClockSampler(local)
@@ -486,7 +489,7 @@ def main():
                            "l2_policy": f"inputs larger than L2 ({B * N * 4 / 1e6:.0f} MB wave, >2 GB of activations per step)",
                            "timing": "CUDA events on the launch stream, max over ranks"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * N * 4, "d2h_bytes_per_step": B * N * 4,
-                        "ms_per_step": ms_e2e / args.steps},
+                        "ms_per_step": ms_e2e / args.steps, "sub_batches": e2e_chunks},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
                 "all_three_product_form": alt, "single_product_last_layer_form": alt1, "parity": PARITY_NOTES.get(args.precision)}
         print(json.dumps(line), flush=True)

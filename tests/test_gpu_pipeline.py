@@ -139,6 +139,15 @@ def test_host_buffer_call_equals_device_call():
     torch.cuda.synchronize()
     ref = torch.cat([pipe(h_in[i:i + 3].cuda()).cpu() for i in range(0, B, 3)])
     assert torch.equal(h_out, ref)
+    # explicit (unequal) sub-batch sizes
+    h_out2 = torch.empty_like(h_in).pin_memory()
+    pipe.run_host(h_in, h_out2, chunks=[1, 4, 2])
+    torch.cuda.synchronize()
+    ref2 = torch.cat([pipe(h_in[a:b].cuda()).cpu() for a, b in ((0, 1), (1, 5), (5, 7))])
+    assert torch.equal(h_out2, ref2)
+    with pytest.raises(RuntimeError, match="add up"):
+        pipe.run_host(h_in, h_out2, chunks=[3, 3])
+    assert sum(pipe.suggest_chunks(B, h_in.shape[1], "cuda")) == B
 
 
 def test_online_training_pairs_match_the_offline_stage():

@@ -47,16 +47,50 @@ class PhaseGenPipeline:
             return audio, logmag, phase
         return audio
 
+    def suggest_chunks(self, B, n_samples, device, max_waves=6):
+        """Sub-batch sizes for run_host: a one-wave head and tail (the only copies that are exposed are the first
+        upload and the last download, so they should be small) and middle sub-batches whose tile count in the
+        heaviest convolution fills whole waves of the persistent grid (a sub-batch that spills a few tiles
+        into an extra wave pays for the whole wave).  From the tiling plan of the outermost up convolution."""
+        import ctypes
+        from . import _lib
+        T = self.frames(n_samples)
+        kw = {"precision": self.precision} if self.precision else {}
+        ex = self.model.executor(B, T, device, per_clip=self.per_clip, phase_only=self.phase_only, **kw)
+        out = (ctypes.c_int * 16)()
+        if ex.prec == _lib.PG_PREC_FP32_SIMT or _lib.load().pg_conv_tc_plan(ctypes.byref(ex.up_desc[0]), out, 16) != 0:
+            return [B]
+        n_ntiles, nb, pair, n_cotiles, OS = out[1], out[2], out[4], out[9], out[10]
+        slabs = (n_cotiles // 2 if pair else n_cotiles) * OS * n_ntiles
+        units = 74 if pair else 148
+        cap = lambda waves: max(nb, nb * ((waves * units) // slabs))      # clips whose tiles fill at most `waves` waves
+        edge, mid = cap(1), cap(max_waves)
+        if B <= 2 * edge + nb:
+            return [B]
+        sizes, rest = [edge], B - 2 * edge
+        while rest > 0:
+            sizes.append(min(mid, rest))
+            rest -= sizes[-1]
+        return sizes + [edge]
+
     def run_host(self, host_in, host_out, chunks=4):
         """End-to-end call on HOST buffers (pinned float32 [B, N] in and out): the batch is cut into
-        `chunks` sub-batches whose host->device copy, GPU work and device->host copy overlap on three
-        streams through two persistent device staging slots (no allocation inside the loop), so only the
-        first upload and the last download are exposed.  Returns when every download has been ordered on
-        the current stream (synchronise it before reading host_out)."""
+        sub-batches (`chunks`: how many equal ones, or an explicit list of sizes, e.g. from suggest_chunks)
+        whose host->device copy, GPU work and device->host copy overlap on three streams through two
+        persistent device staging slots (no allocation inside the loop), so only the first upload and the
+        last download are exposed.  Returns when every download has been ordered on the current stream
+        (synchronise it before reading host_out)."""
         if host_in.is_cuda or host_out.is_cuda:
             raise RuntimeError("run_host takes host tensors; call the pipeline directly for device tensors")
         B, N = host_in.shape
-        Bc = -(-B // max(1, chunks))
+        if isinstance(chunks, int):
+            per = -(-B // max(1, chunks))
+            sizes = [min(per, B - c0) for c0 in range(0, B, per)]
+        else:
+            sizes = [int(c) for c in chunks]
+            if sum(sizes) != B or min(sizes) < 1:
+                raise RuntimeError(f"run_host: chunk sizes {sizes} do not add up to the batch of {B}")
+        Bc = max(sizes)
         cur = torch.cuda.current_stream()
         dev = cur.device
         st = getattr(self, "_host_state", None)
@@ -69,9 +103,10 @@ class PhaseGenPipeline:
         s_in, s_out = st["s_in"], st["s_out"]
         s_in.wait_stream(cur)
         s_out.wait_stream(cur)
-        for i, c0 in enumerate(range(0, B, Bc)):
-            sl = slice(c0, min(B, c0 + Bc))
-            n = sl.stop - sl.start
+        c0 = 0
+        for i, n in enumerate(sizes):
+            sl = slice(c0, c0 + n)
+            c0 += n
             k = i & 1
             d_in, d_out = st["d_in"][k][:n], st["d_out"][k][:n]
             if st["consumed"][k] is not None:
