@@ -143,3 +143,19 @@ def test_weights_are_repacked_after_an_update_and_running_stats_move():
     assert not torch.allclose(a, b)
     assert int(net.model.model[4].num_batches_tracked) == 2
     assert not torch.equal(rm, net.model.model[4].running_mean)
+
+
+def test_executor_cache_is_bounded():
+    """Executors (activation buffers + packed weights per batch shape) are cached LRU with a cap: a service that
+    sees many batch shapes does not accumulate device memory, and an evicted shape is simply rebuilt."""
+    import model
+    net = model.UNetModel(8, 16).cuda()
+    net.max_executors = 3
+    x = {T: torch.randn(2, 8, T, device="cuda") for T in (24, 32, 40, 48, 56)}
+    with torch.no_grad():
+        first = net.forward(x[24]).clone()
+        for T in (32, 40, 48, 56):
+            net.forward(x[T])
+        assert len(net._exec) == 3
+        again = net.forward(x[24])                               # evicted, rebuilt
+    assert torch.equal(first, again) and len(net._exec) == 3

@@ -145,6 +145,7 @@ class UNetModel(nn.Module):
     precision = "auto"
     train_precision = "auto"   # precision of forward+backward under autograd (same choices)
     phase_only = False     # compute only out[:, :C] of the last layer (what demo.py:38 / train.py:78 use)
+    max_executors = 8      # executors (activation buffers + packed weights per batch shape) kept alive; oldest evicted
 
     def __init__(self, input_nc, output_nc, norm_layer=nn.BatchNorm2d, gpu_ids=[]):
         super().__init__()
@@ -184,11 +185,10 @@ class UNetModel(nn.Module):
         if c_final is not None and prec != "fp32_simt" and c_final % 128:
             c_final = None      # tensor-core tiles are 128 channels wide; fall back to the full layer
         key = (B, T, str(device), prec, per_clip, c_final, tuple(sorted(kw.items())))
-        ex = self._exec.get(key)
+        ex = self._cached(key)
         if ex is None:
             ex = _unet.UNetExecutor(levels, B, T, device, prec, per_clip, out_channels=c_final, **kw)
-            self._exec[key] = ex
-            self._packed.pop(id(ex), None)
+            self._remember(key, ex)
         self._ensure_packed(ex)
         return ex
 
@@ -200,13 +200,26 @@ class UNetModel(nn.Module):
         if prec.startswith("f16"):
             prec = "bf16x3"     # the fp16 operand modes are inference-only; autograd runs the bf16 fp32-class form
         key = ("train", B, T, str(device), prec, grad_dtype)
-        ex = self._exec.get(key)
+        ex = self._cached(key)
         if ex is None:
             ex = TrainExecutor(levels, B, T, device, prec, grad_dtype=grad_dtype)
-            self._exec[key] = ex
-            self._packed.pop(id(ex), None)
+            self._remember(key, ex)
         self._ensure_packed(ex)
         return ex
+
+    def _cached(self, key):
+        ex = self._exec.pop(key, None)
+        if ex is not None:
+            self._exec[key] = ex                    # most recently used last (dicts keep insertion order)
+        return ex
+
+    def _remember(self, key, ex):
+        self._exec[key] = ex
+        self._packed.pop(id(ex), None)
+        while len(self._exec) > max(1, int(self.max_executors)):
+            old_key = next(iter(self._exec))
+            old = self._exec.pop(old_key)
+            self._packed.pop(id(old), None)
 
     def _param_grads(self, ex):
         """Gradients in the order of self.parameters(): conv weights in torch layout, norm gamma/beta."""
