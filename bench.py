@@ -216,7 +216,6 @@ def run_train(args):
         loss_ev[k] = torch.cuda.Event(); loss_ev[k].record()
         e2e_i[0] += 1
 
-    e2e_chunks = pipe.suggest_chunks(B, N, dev) if args.e2e_chunks == 0 else args.e2e_chunks
     for _ in range(W):
         step_resident()
     sampler = ClockSampler(local)

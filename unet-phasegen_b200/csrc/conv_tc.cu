@@ -136,8 +136,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
 
     if (warp == 0) {
         // ===================================================================== TMA producer
-        if (lane == 0) {
-            uint32_t a_it = 0, b_it = 0;
+        // Warp-uniform like the MMA warp (every lane runs the loop, one elected lane issues): the TMA operands
+        // live in uniform registers instead of going through an R2UR waterfall per UTMALDG, and the ring
+        // indices are counters (no runtime division).  With one or two products per MAC a weight tile is
+        // consumed in 640-770 tensor cycles, so the producer's per-tap cost is on the critical path.
+        {
+            uint32_t b_it = 0;
+            int a_slot = 0; uint32_t a_ph = 0;
             const uint32_t grp_bytes = (uint32_t)nb_cta * pl.strip_rows * 128u;   // one merged group's strips in this CTA
             const uint32_t a_bytes = a_planes * kATileBytes;
             const uint32_t b_bytes = b_planes * (uint32_t)bPlane;
@@ -154,42 +159,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                             const int s = b_it & 1; const uint32_t ph = (b_it >> 1) & 1;
                             mbar_wait(emptyB + s, ph ^ 1);
                             uint8_t* dst = b_base + (size_t)s * b_planes * bPlane;
-                            if (PAIR) { if (rank == 0) mbar_expect_tx(fullB + s, 2 * b_bytes); }   // both CTAs' halves
-                            else mbar_expect_tx(fullB + s, b_bytes);
-                            for (int mg = 0; mg < pl.mgroups; ++mg) {      // one box per merged group (its clips are contiguous)
-                                uint8_t* dg = dst + (size_t)mg * grp_bytes;
-                                const int cg = clip0 + mg * nb_grp;
-                                if (PAIR) {
-                                    tma_load_4d_pair(dg, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
-                                    if (x_lo) tma_load_4d_pair(dg + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
-                                } else {
-                                    tma_load_4d(dg, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
-                                    if (x_lo) tma_load_4d(dg + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
+                            if (elect_one()) {
+                                if (PAIR) { if (rank == 0) mbar_expect_tx(fullB + s, 2 * b_bytes); }   // both CTAs' halves
+                                else mbar_expect_tx(fullB + s, b_bytes);
+                                for (int mg = 0; mg < pl.mgroups; ++mg) {      // one box per merged group (its clips are contiguous)
+                                    uint8_t* dg = dst + (size_t)mg * grp_bytes;
+                                    const int cg = clip0 + mg * nb_grp;
+                                    if (PAIR) {
+                                        tma_load_4d_pair(dg, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
+                                        if (x_lo) tma_load_4d_pair(dg + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
+                                    } else {
+                                        tma_load_4d(dg, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
+                                        if (x_lo) tma_load_4d(dg + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
+                                    }
                                 }
                             }
+                            __syncwarp();
                             ++b_it;
                         }
                         for (int j = 0; j < grp.n_taps; ++j) {
-                            const ConvTap tp = pl.taps[tc.phase][grp.first_tap + j];
-                            const int s = a_it % nA; const uint32_t ph = (a_it / nA) & 1;
+                            const int w_idx = pl.taps[tc.phase][grp.first_tap + j].w_idx;
+                            const int s = a_slot; const uint32_t ph = a_ph;
                             mbar_wait(emptyA + s, ph ^ 1);
-                            if (!PAIR) mbar_expect_tx(fullA + s, a_bytes);
-                            else if (rank == 0) mbar_expect_tx(fullA + s, 2 * a_bytes);
                             uint8_t* dst = a_base + (size_t)s * a_planes * kATileBytes;
-                            auto load_w = [&](uint8_t* d, const CUtensorMap* m, int c0, int c1) {
-                                if (PAIR) tma_load_3d_pair(d, m, fullA + s, c0, c1, tp.w_idx);
-                                else tma_load_3d(d, m, fullA + s, c0, c1, tp.w_idx);
-                            };
-                            if (prm.a_mn) {     // two {64 co, 64 ci-rows} boxes: MN-major atom stacks, 8 KB apart
-                                for (int h = 0; h < 2; ++h) {
-                                    load_w(dst + h * 8192, &map_w_hi, tc.co_tile * 128 + h * 64, ch * 64);
-                                    if (w_lo) load_w(dst + kATileBytes + h * 8192, &map_w_lo, tc.co_tile * 128 + h * 64, ch * 64);
+                            if (elect_one()) {
+                                if (!PAIR) mbar_expect_tx(fullA + s, a_bytes);
+                                else if (rank == 0) mbar_expect_tx(fullA + s, 2 * a_bytes);
+                                auto load_w = [&](uint8_t* d, const CUtensorMap* m, int c0, int c1) {
+                                    if (PAIR) tma_load_3d_pair(d, m, fullA + s, c0, c1, w_idx);
+                                    else tma_load_3d(d, m, fullA + s, c0, c1, w_idx);
+                                };
+                                if (prm.a_mn) {     // two {64 co, 64 ci-rows} boxes: MN-major atom stacks, 8 KB apart
+                                    for (int h = 0; h < 2; ++h) {
+                                        load_w(dst + h * 8192, &map_w_hi, tc.co_tile * 128 + h * 64, ch * 64);
+                                        if (w_lo) load_w(dst + kATileBytes + h * 8192, &map_w_lo, tc.co_tile * 128 + h * 64, ch * 64);
+                                    }
+                                } else {
+                                    load_w(dst, &map_w_hi, ch * 64, tc.co_tile * 128);
+                                    if (w_lo) load_w(dst + kATileBytes, &map_w_lo, ch * 64, tc.co_tile * 128);
                                 }
-                            } else {
-                                load_w(dst, &map_w_hi, ch * 64, tc.co_tile * 128);
-                                if (w_lo) load_w(dst + kATileBytes, &map_w_lo, ch * 64, tc.co_tile * 128);
                             }
-                            ++a_it;
+                            __syncwarp();
+                            if (++a_slot == nA) { a_slot = 0; a_ph ^= 1; }
                         }
                     }
                 }
@@ -200,7 +211,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
         // The whole warp runs this loop with warp-uniform control flow; only the tcgen05 instructions
         // themselves are issued by one elected lane (always the same one, so tcgen05.commit tracks them).
         if (rank == 0) {
-            uint32_t a_it = 0, b_it = 0, t_it = 0;
+            uint32_t b_it = 0, t_it = 0;
+            int a_slot = 0; uint32_t a_ph = 0;
             // operand format field: 1 = bf16, 0 = fp16 (bits [7,10) for A, [10,13) for B)
             const int n_mma = pl.merged ? nb_grp * pl.strip_rows : pl.n_tile;
             const int n_loop = pl.merged ? pl.mgroups : pl.nb;    // merged: one MMA covers every clip of a group
@@ -235,7 +247,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                         const uint32_t b_lo = b_hi + bPlane;
                         for (int j = 0; j < grp.n_taps; ++j) {
                             const ConvTap tp = pl.taps[tc.phase][grp.first_tap + j];
-                            const int as = a_it % nA; const uint32_t aph = (a_it / nA) & 1;
+                            const int as = a_slot; const uint32_t aph = a_ph;
                             mbar_wait(fullA + as, aph);
                             tc_fence_after();
                             const uint32_t a_hi = smem_u32(a_base + (size_t)as * a_planes * kATileBytes);
@@ -266,7 +278,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                             }
                             accumulate = 1; accumulate_rest = 1;
                             commit(emptyA + as);
-                            ++a_it;
+                            if (++a_slot == nA) { a_slot = 0; a_ph ^= 1; }
                         }
                         commit(emptyB + bs);
                         ++b_it;

@@ -89,19 +89,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
     const int n_bblk = PAIR ? prm.nci / 128 : prm.nci / 64;       // 64-channel X blocks this CTA loads
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
+        {   // warp-uniform producer: every lane runs the loop, one elected lane issues (see conv_tc.cu)
+            int st_i = 0; uint32_t st_ph = 0;
             const uint32_t bytes = (uint32_t)stage_bytes;
             for (int item = item0; item < n_items; item += item_step) {
                 const WgItem w = wg_decode(prm, item);
                 const ConvGroup grp = pl.groups[w.phase][w.group];
-                for (int kc = 0; kc < n_kchunks; ++kc, ++it) {
-                    const int b = kc / prm.n_mchunks, m0 = (kc % prm.n_mchunks) * prm.R;
-                    const int s = it % prm.n_stages; const uint32_t ph = (it / prm.n_stages) & 1;
+                int b = 0, mc = 0;
+                for (int kc = 0; kc < n_kchunks; ++kc) {
+                    const int m0 = mc * prm.R;
+                    const int s = st_i; const uint32_t ph = st_ph;
                     mbar_wait(empty + s, ph ^ 1);
+                    uint8_t* st = smem + (size_t)s * stage_bytes;
+                    if (elect_one()) {
                     if (!PAIR) mbar_expect_tx(full + s, bytes);
                     else if (rank == 0) mbar_expect_tx(full + s, 2 * bytes);      // both CTAs' operands
-                    uint8_t* st = smem + (size_t)s * stage_bytes;
                     const int co0 = (PAIR ? w.co_tile * 2 + rank : w.co_tile) * 128;
                     const int ci0 = w.ci_tile * prm.nci + (PAIR ? rank * (prm.nci / 2) : 0);
                     for (int pln = 0; pln < planes; ++pln) {
@@ -118,12 +120,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
                             else tma_load_4d(bq + (size_t)h * prm.RB * 128, mx, full + s, ci0 + h * 64, grp.parity, m0 + grp.row0, b);
                         }
                     }
+                    }
+                    __syncwarp();
+                    if (++st_i == prm.n_stages) { st_i = 0; st_ph ^= 1; }
+                    if (++mc == prm.n_mchunks) { mc = 0; ++b; }
                 }
             }
         }
     } else if (warp == 1) {
         if (rank == 0) {   // whole warp, warp-uniform control flow; one elected lane issues the tcgen05 instructions
-            uint32_t it = 0, n_it = 0;
+            uint32_t n_it = 0;
+            int st_i = 0; uint32_t st_ph = 0;
             const uint32_t idesc = (make_idesc_bf16_mn(prm.nci) & ~(0x1Fu << 24)) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);   // M = 256 for pairs
             auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc_flag) {
                 if (elect_one()) { if (PAIR) umma_bf16_pair(d, da, db, idesc, acc_flag); else umma_bf16(d, da, db, idesc, acc_flag); }
@@ -138,8 +145,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
                 const ConvGroup grp = pl.groups[w.phase][w.group];
                 mbar_wait_sleep(accEmpty, (n_it & 1) ^ 1, 200);
                 tc_fence_after();
-                for (int kc = 0; kc < n_kchunks; ++kc, ++it) {
-                    const int s = it % prm.n_stages; const uint32_t ph = (it / prm.n_stages) & 1;
+                for (int kc = 0; kc < n_kchunks; ++kc) {
+                    const int s = st_i; const uint32_t ph = st_ph;
                     mbar_wait(full + s, ph);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
@@ -165,6 +172,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
                         }
                     }
                     commit(empty + s);
+                    if (++st_i == prm.n_stages) { st_i = 0; st_ph ^= 1; }
                 }
                 commit(accFull);
             }
