@@ -52,7 +52,7 @@ def main():
                           taps_per_group=a.tpg, max_clips_per_tile=a.nb)
         y = torch.empty(a.B, d.L_out, C_out, device="cuda")
         st = torch.empty(a.B, ops.conv_stat_parts(d), C_out, 4, device="cuda")
-        terms = {"bf16x3": 3, "f16x3": 3, "f16x2": 2, "bf16": 1}[a.prec]
+        terms = {"bf16x3": 3, "f16x3": 3, "f16x2": 2, "bf16": 1, "f16": 1}[a.prec]
         three = terms
         run = lambda: ops.conv_tc(d, x, xl if terms >= 2 else None, hi, lo if terms == 3 else None, y, st)
         for _ in range(2):
