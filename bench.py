@@ -216,11 +216,11 @@ def run_train(args):
         loss_ev[k] = torch.cuda.Event(); loss_ev[k].record()
         e2e_i[0] += 1
 
-    for _ in range(W):
-        step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()                                        # nvidia-smi needs ~0.1 s to deliver its first sample: start it
+    for _ in range(W):                                         # before the warm-up so the timed region is covered
+        step_resident()
     l0 = _lib.launches
     ms = timed(step_resident, args.steps)
     launches = _lib.launches - l0
@@ -359,11 +359,11 @@ def main():
         pipe.run_host(host_in, host_out, chunks=e2e_chunks)
 
     e2e_chunks = pipe.suggest_chunks(B, N, dev) if args.e2e_chunks == 0 else args.e2e_chunks
-    for _ in range(W):
-        step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()                                        # nvidia-smi needs ~0.1 s to deliver its first sample: start it
+    for _ in range(W):                                         # before the warm-up so the timed region is covered
+        step_resident()
     l0 = _lib.launches
     ms = timed(step_resident, args.steps)
     launches = _lib.launches - l0
