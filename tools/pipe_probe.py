@@ -36,3 +36,15 @@ for it in range(6):
         agg[n] = agg.get(n, 0.0) + a.elapsed_time(b)
     print(f"iter {it}: total {s0.elapsed_time(s1):.2f} ms, cpu enqueue {1e3 * (t1 - t0):.2f} ms, cudaMallocs {seg1 - seg0}; " +
           ", ".join(f"{k} {v:.3f}" for k, v in agg.items()), flush=True)
+if B <= 8:
+    g = pipe.capture(B, N)
+    for _ in range(3):
+        g(wave)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(20):
+        g(wave)
+    s1.record(); torch.cuda.synchronize()
+    print(f"graph replay: {s0.elapsed_time(s1) / 20:.3f} ms GPU per call, {1e3 * (time.perf_counter() - t0) / 20:.3f} ms wall per call (eager above)", flush=True)

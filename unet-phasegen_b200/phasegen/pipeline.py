@@ -11,6 +11,18 @@ from . import ops
 from ._lib import PG_DT_F32, PG_SPEC_POLAR_LOG, PG_STFT_LOGMAG
 
 
+class _GraphedPipeline:
+    def __init__(self, graph, static_in, static_out):
+        self.graph, self.static_in, self.static_out = graph, static_in, static_out
+
+    def __call__(self, wave):
+        if tuple(wave.shape) != tuple(self.static_in.shape) or not wave.is_cuda:
+            raise RuntimeError(f"graphed pipeline was captured for a CUDA tensor of shape {tuple(self.static_in.shape)}")
+        self.static_in.copy_(wave, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+
 class PhaseGenPipeline:
     def __init__(self, model, n_fft, hop, precision=None, per_clip=True, phase_only=True, normalize=True):
         ops.check_stft_geometry(n_fft, hop)
@@ -46,6 +58,28 @@ class PhaseGenPipeline:
         if return_intermediates:
             return audio, logmag, phase
         return audio
+
+    def capture(self, B, n_samples, device=None, warmup=2):
+        """CUDA-graph form of the pipeline for one fixed shape: the ~25 launches of a call are recorded once and
+        replayed with a single `cudaGraphLaunch`, which removes the per-launch host cost (0.8 ms of Python/ctypes
+        per call -- comparable to the 1.3 ms of GPU time of a single 4 s clip).  Returns a callable
+        ``g(wave) -> audio``: `wave` is copied into the graph's static input buffer, the result is the graph's
+        static output buffer (valid until the next call; clone it to keep it).  Weights are read from the
+        executor's packed planes at replay time: call ``capture`` again after changing the model's weights."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        static_in = torch.zeros(B, n_samples, device=dev, dtype=torch.float32)
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                   # warm-up off the capture: executors, packed weights, smem opt-ins
+            for _ in range(max(1, warmup)):
+                self(static_in)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = self(static_in)
+        return _GraphedPipeline(graph, static_in, static_out)
 
     def suggest_chunks(self, B, n_samples, device, max_waves=6):
         """Sub-batch sizes for run_host: a one-wave head and tail (the only copies that are exposed are the first
