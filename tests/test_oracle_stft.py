@@ -83,3 +83,33 @@ def test_griffin_lim_keeps_reference_quirk():
     assert a8.shape == a1.shape and s8.shape == mag.shape
     assert np.isfinite(a8).all() and np.isfinite(l8) and np.isfinite(l1)
     assert abs(np.max(np.abs(a8)) - 1.0) < 1e-6
+
+
+def test_window_is_the_one_librosa_asks_scipy_for():
+    """librosa.stft/istft build their window with scipy.signal.get_window('hann', n_fft, fftbins=True); scipy IS in this
+    image, so the oracle's window is pinned to the dependency's own provider."""
+    from scipy.signal import get_window
+    for n in (256, 512, 1024, 2048):
+        assert np.array_equal(stft_np.hann_periodic(n), get_window("hann", n, fftbins=True)) or \
+            np.max(np.abs(stft_np.hann_periodic(n) - get_window("hann", n, fftbins=True))) < 1e-15
+
+
+@pytest.mark.parametrize("n_fft", [512, 1024, 2048])
+def test_stft_istft_match_scipy(n_fft):
+    """A third, independent implementation (scipy.signal.stft / istft with the librosa conventions: periodic Hann,
+    hop n_fft/4, 'even' = reflect boundary extension of n_fft/2, no zero padding, unscaled spectrum).  scipy scales
+    its spectrum by 1/sum(window), undone here; frames and bins then agree to rounding, and so do the inverses."""
+    from scipy import signal
+    hop = n_fft // 4
+    rng = np.random.default_rng(n_fft + 1)
+    y = rng.standard_normal(hop * 37)
+    win = signal.get_window("hann", n_fft, fftbins=True)
+    _, _, Z = signal.stft(y, window=win, nperseg=n_fft, noverlap=n_fft - hop, nfft=n_fft, boundary="even", padded=False,
+                          return_onesided=True)
+    S = stft_np.stft(y, n_fft, hop)
+    assert Z.shape == S.shape
+    assert rel_l2(Z * win.sum(), S) < 1e-12
+    _, back = signal.istft(S / win.sum(), window=win, nperseg=n_fft, noverlap=n_fft - hop, nfft=n_fft, boundary=True,
+                           input_onesided=True)
+    mine = stft_np.istft(S, hop)
+    assert rel_l2(back[:len(mine)], mine) < 1e-10
