@@ -67,8 +67,12 @@ int pg_stft_pairs(const float* wave, int B, int N, int n_fft, int hop, const flo
  * a = magnitude; in both polar modes b may be NULL for zero phase: the "no phase" reconstruction of train.py:86).  Inputs frame-major [B][T][n_fft/2]
  * (bins 1..n_fft/2); wave [B][(T-1)*hop].  peak [B] (max |wave|) and nonfinite [B] may be NULL. */
 enum { PG_SPEC_POLAR_LOG = 0, PG_SPEC_CARTESIAN = 1, PG_SPEC_POLAR_MAG = 2 };
+/* b_scale_shift (may be NULL): float2 (scale, shift) per bin, [B][n_fft/2] when b_ss_per_clip else [n_fft/2]; the kernel
+ * reads in_b as in_b*scale + shift.  This is the train-mode norm that ends the U-Net (model.py:83,91) applied while the
+ * last convolution's raw output is read, so that tensor is never re-written normalised. */
 int pg_istft(const float* in_a, const float* in_b, int mode, int B, int T, int n_fft, int hop,
-             const float* twiddle, float* wave, float* peak, int* nonfinite, pg_stream stream);
+             const float* twiddle, float* wave, float* peak, int* nonfinite,
+             const float* b_scale_shift, int b_ss_per_clip, pg_stream stream);
 int pg_peak_normalize(float* wave, const float* peak, int B, int N, pg_stream stream);
 
 /* ---------------------------------------------------------------- U-Net layers
@@ -103,6 +107,9 @@ typedef struct pg_conv_desc {
                                  reuses that layer's forward weight planes, no second packing */
     int tc_cta_pair;          /* tensor-core path: 256-channel tiles on CTA pairs (cta_group::2 MMAs, each SM reads half
                                  of the activation strip): 0 = auto (C_out % 256 == 0), 1 = off, 2 = required */
+    int tc_whole_clip;        /* tensor-core path, planning only (pg_conv_tc_plan): tile = every output position of a clip
+                                 (all phases x position tiles side by side in the accumulator); pg_conv_tc sets it itself
+                                 from the epilogue mode */
 } pg_conv_desc;
 
 /* weights: torch layout (Conv1d [C_out][C_in][k], ConvTranspose1d [C_in][C_out][k])
@@ -114,14 +121,43 @@ int pg_pack_weight(const float* w, int kind, int C_in, int C_out, int k, uint16_
 /* tcgen05 implicit GEMM.  x: bf16 planes [B][in_rows][in_ld]; y fp32 [B][out_rows][out_ld];
  * stats (may be NULL): float4 {n, mean, M2, 0} [B][P][C_out], P = pg_conv_stat_parts(). */
 /* fp32 -> 16-bit hi/lo planes (fmt = PG_FMT_*), elementwise (weights kept in the packed layout need no re-ordering) */
-int pg_cast_split(const float* src, int64_t n, uint16_t* hi, uint16_t* lo, int fmt, pg_stream stream);
+int pg_cast_split(const float* src, int64_t n, uint16_t* hi, uint16_t* lo, int fmt, int* range_flag, pg_stream stream);
+
+/* Destination of an activated tensor (the operand buffer of a consumer layer, or an fp32 tensor). */
+typedef struct pg_act_dst {
+    void* hi; void* lo;       /* PG_DT_F32: hi = float*; PG_DT_{BF16,F16}_SPLIT: two 16-bit planes; PG_DT_{BF16,F16}: hi only */
+    int64_t batch_stride;     /* elements between clips */
+    int ld, ch_off;           /* row pitch and first channel written (skip-concat offset, model.py:113) */
+    int dtype;                /* PG_DT_* */
+    float slope;              /* 0 = ReLU (model.py:82), 0.2 = LeakyReLU (model.py:80), 1 = identity */
+    int* range_flag;          /* may be NULL; device int, bit 0 is OR-ed in when a value written to an FP16 plane lies outside
+                                 the fp16 range (|v| > 65504) or is not finite: the fp16 operand modes are then invalid for
+                                 this input and the caller must fall back to the bf16 planes (same bytes, fp32 range) */
+} pg_act_dst;
+
+/* Fused epilogue of pg_conv_tc (model.py:80-83,113 inside the convolution kernel).
+ *   PG_EPI_RAW      y fp32 + statistics records (batch statistics need a second pass: pg_bn_finalize + pg_bn_act)
+ *   PG_EPI_ACT      layer without norm (model.py:90,96): act(conv) written straight into the consumers' operand planes
+ *   PG_EPI_NORM_ACT train-mode norm with the clip's OWN statistics (what the demo.py:33-42 batch-1 loop computes), then
+ *                   the activation(s): statistics are complete inside the tile because the tile holds every output
+ *                   position of the clip (pg_conv_epilogue_supported says whether it fits); y and stats are not written */
+enum { PG_EPI_RAW = 0, PG_EPI_ACT = 1, PG_EPI_NORM_ACT = 2 };
+typedef struct pg_conv_epilogue {
+    int mode;
+    const float* gamma; const float* beta;   /* [C_out], may be NULL (1, 0) */
+    float eps;
+    pg_act_dst dst0, dst1;                   /* dst1.dtype = PG_DT_NONE when unused */
+    float* scale_shift;                      /* NORM_ACT, may be NULL: float2 [B][C_out], the (scale, shift) applied */
+} pg_conv_epilogue;
+int pg_conv_epilogue_supported(const pg_conv_desc* d, int mode);
 
 int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo,
-               const uint16_t* w_hi, const uint16_t* w_lo, float* y, float* stats, pg_stream stream);
+               const uint16_t* w_hi, const uint16_t* w_lo, float* y, float* stats,
+               const pg_conv_epilogue* epilogue /* NULL = PG_EPI_RAW */, pg_stream stream);
 int pg_conv_stat_parts(const pg_conv_desc* d);
 /* Tiling plan of pg_conv_tc for a layer, host-only: out[16] = {n_tile, n_ntiles, clips per tile, strip rows, CTA pair,
  * merged clips, MMA groups per weight tile, TMEM accumulator stages, C_in/64, C_out/128, output phases, input
- * parities, taps of phase 0, of phase 1, tap groups of phase 0, of phase 1}. */
+ * parities, taps of phase 0, of phase 1, tap groups of phase 0, of phase 1 [, whole-clip tile]} (the 17th when n_out >= 17). */
 int pg_conv_tc_plan(const pg_conv_desc* d, int* out, int n_out);
 /* exact fp32 on CUDA cores; x fp32 [B][in_rows][in_ld], w_simt from pg_pack_weight. */
 int pg_conv_simt(const pg_conv_desc* d, const float* x, const float* w_simt, float* y, pg_stream stream);
@@ -134,13 +170,11 @@ int pg_channel_stats(const float* y, int B, int L, int C, int rows, int ld, floa
 int pg_bn_finalize(const float* stats, int B, int P, int C, int per_clip, const float* gamma,
                    const float* beta, float eps, float* scale_shift, float* mean_var, pg_stream stream);
 
-typedef struct pg_act_dst {
-    void* hi; void* lo;       /* PG_DT_F32: hi = float*; PG_DT_{BF16,F16}_SPLIT: two 16-bit planes; PG_DT_{BF16,F16}: hi only */
-    int64_t batch_stride;     /* elements between clips */
-    int ld, ch_off;           /* row pitch and first channel written (skip-concat offset, model.py:113) */
-    int dtype;                /* PG_DT_* */
-    float slope;              /* 0 = ReLU (model.py:82), 0.2 = LeakyReLU (model.py:80), 1 = identity */
-} pg_act_dst;
+/* eval-mode norm (nn.BatchNorm after .eval(); the reference never calls it, kept for API parity): scale/shift from the
+ * running statistics, replicated into G groups so that per-clip consumers can index it by clip. */
+int pg_bn_from_running(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
+                       float eps, int C, int G, float* scale_shift, float* mean_var, pg_stream stream);
+
 /* v = y*scale+shift (scale_shift NULL = identity), then per destination act(v).  C = number
  * of leading channels of y processed. */
 int pg_bn_act(const float* y, int B, int L, int C, int rows, int ld, const float* scale_shift,
@@ -148,7 +182,8 @@ int pg_bn_act(const float* y, int B, int L, int C, int rows, int ld, const float
 
 /* [B][R][S] fp32 -> [B][S][R] fp32 and/or 16-bit hi/lo planes (fmt = PG_FMT_*) (reference [B,C,T] <-> channels-last). */
 int pg_transpose(const float* src, int B, int R, int S, int64_t src_batch_stride, float* dst,
-                 uint16_t* dst_hi, uint16_t* dst_lo, int64_t dst_batch_stride, int dst_ld, int fmt, pg_stream stream);
+                 uint16_t* dst_hi, uint16_t* dst_lo, int64_t dst_batch_stride, int dst_ld, int fmt, int* range_flag /* may be NULL */,
+                 pg_stream stream);
 
 /* ---------------------------------------------------------------- training step (train.py:37-62)
  * Replace loss.backward() (autograd through cuDNN, train.py:61), the loss of train.py:45-60 and

@@ -26,13 +26,14 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/phasegen.h but not exported"
     assert set(_lib.EXPORTS) == set(syms), "ctypes binding and header disagree"
-    assert _lib.load().pg_abi_version() == 2
+    assert _lib.load().pg_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():
     from phasegen import _lib
-    assert ctypes.sizeof(_lib.ConvDesc) == 20 * 4
-    assert ctypes.sizeof(_lib.ActDst) == 8 + 8 + 8 + 4 * 4
+    assert ctypes.sizeof(_lib.ConvDesc) == 21 * 4
+    assert ctypes.sizeof(_lib.ActDst) == 8 + 8 + 8 + 4 * 4 + 8          # + range_flag pointer
+    assert ctypes.sizeof(_lib.ConvEpilogue) == 8 + 8 + 8 + 8 + 2 * 48 + 8   # mode(+pad), gamma, beta, eps(+pad), dst0, dst1, scale_shift
 
 
 def test_error_reporting_without_gpu_call():

@@ -21,10 +21,10 @@ def plan(layer, C, T, B, prec, **kw):
     L_in = lengths(T)[layer]
     rows = (L_in + 7) // 8 * 8
     d = ops.conv_desc(kind, B, C * cim, C * com, L_in, k, s, p, rows, C * cim, _lib.PRECISIONS[prec], **kw)
-    out = (ctypes.c_int * 16)()
-    rc = _lib.load().pg_conv_tc_plan(ctypes.byref(d), out, 16)
+    out = (ctypes.c_int * 17)()
+    rc = _lib.load().pg_conv_tc_plan(ctypes.byref(d), out, 17)
     assert rc == 0, _lib.last_error()
-    return dict(zip(KEYS, out)), d
+    return dict(zip(KEYS + ("whole_clip",), out)), d
 
 
 def test_inference_shapes_use_pairs_and_full_width_tiles():
@@ -76,3 +76,28 @@ def test_plan_options_and_errors():
     d = ops.conv_desc(0, 4, 64, 128, 64, 8, 1, 2, 64, 64, _lib.PG_PREC_BF16X3)
     assert _lib.load().pg_conv_tc_plan(ctypes.byref(d), out, 16) == 0 and out[4] == 0
     assert _lib.load().pg_conv_tc_plan(ctypes.byref(d), out, 8) < 0
+
+
+def test_whole_clip_tiles_for_the_fused_norm_epilogue():
+    """BASELINE inference shape (C 512, T 696), bench precisions: which layers hold a whole clip per tile."""
+    from phasegen import _lib, ops
+    d2, _ = plan("d2", 512, 696, 256, "f16x3", whole_clip=1)          # 346 positions = 2 x 176 columns, one TMEM stage
+    assert (d2["whole_clip"], d2["n_ntiles"], d2["OS"], d2["nb"], d2["acc_stages"]) == (1, 2, 1, 1, 1)
+    u2, _ = plan("u2", 512, 696, 256, "f16x2", whole_clip=1)          # same column budget as its two-clip tiles
+    assert (u2["whole_clip"], u2["n_ntiles"], u2["nb"], u2["acc_stages"]) == (1, 2, 1, 1)
+    u3, _ = plan("u3", 512, 696, 256, "f16x3", whole_clip=1)          # both output phases side by side
+    assert (u3["whole_clip"], u3["OS"], u3["n_ntiles"], u3["n_tile"], u3["acc_stages"]) == (1, 2, 1, 176, 1)
+    u4, _ = plan("u4", 512, 696, 256, "f16x3", whole_clip=1)          # two phases of 96 columns: un-merged, double-buffered
+    assert (u4["whole_clip"], u4["merged"], u4["nb"], u4["acc_stages"]) == (1, 0, 1, 2)
+    d3, d = plan("d3", 512, 696, 256, "f16x3", whole_clip=1)          # one part: the ordinary tile already is a whole clip
+    assert (d3["whole_clip"], d3["n_ntiles"], d3["OS"]) == (0, 1, 1)
+    lib = _lib.load()
+    assert lib.pg_conv_epilogue_supported(ctypes.byref(d), _lib.PG_EPI_NORM_ACT) == 1
+    _, du1 = plan("u1", 512, 696, 256, "f16x2")
+    assert lib.pg_conv_epilogue_supported(ctypes.byref(du1), _lib.PG_EPI_NORM_ACT) == 0      # 704 columns
+    assert lib.pg_conv_epilogue_supported(ctypes.byref(du1), _lib.PG_EPI_ACT) == 1
+    # training shape: merged single-phase tiles already hold whole clips; two-phase layers are un-merged on request
+    d3t, _ = plan("d3", 1024, 128, 32, "bf16", whole_clip=1)
+    assert d3t["merged"] == 1 and d3t["whole_clip"] == 0
+    u3t, _ = plan("u3", 1024, 128, 32, "bf16", whole_clip=1)
+    assert u3t["merged"] == 0 and u3t["whole_clip"] == 1

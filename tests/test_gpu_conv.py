@@ -167,3 +167,104 @@ def test_conv_argument_errors():
     d = ops.conv_desc(0, 1, 64, 128, 32, 8, 3, 2, 32, 64, ops.PG_PREC_BF16X3)
     with pytest.raises(RuntimeError, match="stride"):
         ops.conv_tc(d, x, x, w, w, y, None)
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "f16x3", "f16x2"])
+@pytest.mark.parametrize("layer,C,L_in,B,pair", [
+    ("d1", 128, 696, 5, 0), ("d4", 128, 171, 7, 0), ("d1", 64, 136, 3, 1),                      # no norm: PG_EPI_ACT
+    ("d2", 128, 349, 5, 0), ("d3", 128, 346, 5, 0), ("u4", 128, 85, 5, 0), ("u3", 128, 171, 5, 0), ("u2", 128, 346, 5, 0),
+    ("u2", 64, 346, 3, 1), ("u3", 64, 31, 6, 1), ("d3", 128, 66, 9, 0), ("u4", 128, 15, 9, 0), ("d2", 128, 69, 7, 0)])
+def test_tc_conv_fused_epilogues(layer, C, L_in, B, pair, prec):
+    """The fused epilogues (PG_EPI_ACT; PG_EPI_NORM_ACT with whole-clip tiles: two position tiles, two output phases,
+    merged short clips, CTA pairs and single CTAs) against the two-pass form built from the exact SIMT convolution:
+    per-clip statistics, affine, LeakyReLU / ReLU fan-out, written at a channel offset into wider operand buffers."""
+    from phasegen import ops
+    from phasegen._lib import PG_DT_BF16_SPLIT, PG_DT_F16_SPLIT, PG_EPI_ACT, PG_EPI_NORM_ACT, PRECISIONS
+    kind, k, s, p, C_in, C_out, rows, x, w = _case(layer, C, L_in, B, seed=5)
+    has_norm = layer not in ("d1", "d4")
+    mode = PG_EPI_NORM_ACT if has_norm else PG_EPI_ACT
+    f16 = prec.startswith("f16")
+    pdt = torch.float16 if f16 else torch.bfloat16
+    d = ops.conv_desc(kind, B, C_in, C_out, L_in, k, s, p, rows, C_in, PRECISIONS[prec], taps_per_group=16, cta_pair=pair)
+    if not ops.conv_epilogue_supported(d, mode):
+        # only case: single-CTA tiles (128 output channels) load full-width strips; two of them x two planes x two slots
+        # do not fit shared memory, so the executor keeps the two-pass form for that layer
+        assert (layer, pair, L_in) == ("u2", 1, 346) and prec != "bf16"
+        return
+    ds = ops.conv_desc(kind, B, C_in, C_out, L_in, k, s, p, rows, C_in, ops.PG_PREC_FP32_SIMT)
+    hi, lo, ws = ops.pack_weight(w, kind, True, True, plane_dtype=pdt)
+    xh = x.to(pdt); xl = (x - xh.float()).to(pdt)
+    ys = torch.empty(B, ds.L_out, C_out, device="cuda")
+    ops.conv_simt(ds, x, ws, ys)
+    g = torch.Generator().manual_seed(6)
+    gamma = (1.0 + 0.2 * torch.randn(C_out, generator=g)).cuda()
+    beta = (0.3 * torch.randn(C_out, generator=g)).cuda()
+    h = ys.double()
+    if has_norm:
+        mean = h.mean(1, keepdim=True); var = h.var(1, unbiased=False, keepdim=True)
+        h = (h - mean) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double()
+    L_out, rows_o = ds.L_out, (ds.L_out + 7) // 8 * 8
+    wide, off = 2 * C_out, C_out                                  # second destination: right half of a concat buffer
+    flag = torch.zeros(1, device="cuda", dtype=torch.int32)
+    dt = PG_DT_F16_SPLIT if f16 else PG_DT_BF16_SPLIT
+    a_hi = torch.zeros(B, rows_o, C_out, device="cuda", dtype=pdt); a_lo = torch.zeros_like(a_hi)
+    c_hi = torch.zeros(B, rows_o, wide, device="cuda", dtype=pdt); c_lo = torch.zeros_like(c_hi)
+    epi = ops.conv_epilogue(mode, ops.act_dst(a_hi, a_lo, rows_o * C_out, C_out, 0, dt, 0.2, flag),
+                            ops.act_dst(c_hi, c_lo, rows_o * wide, wide, off, dt, 0.0, flag),
+                            gamma if has_norm else None, beta if has_norm else None, 1e-5)
+    ops.conv_tc(d, xh, xl, hi, lo if prec.endswith("x3") else None, None, None, epi)
+    torch.cuda.synchronize()
+    tol = 2e-3 if prec == "f16x2" else 2e-4
+    got_a = (a_hi.double() + a_lo.double())[:, :L_out]
+    got_c = (c_hi.double() + c_lo.double())[:, :L_out, off:]
+    ref_a = torch.where(h > 0, h, 0.2 * h); ref_c = torch.clamp(h, min=0)
+    assert float((got_a - ref_a).norm() / ref_a.norm()) < tol, (layer, "leaky destination")
+    assert float((got_c - ref_c).norm() / ref_c.norm()) < tol, (layer, "relu destination at a channel offset")
+    assert float(c_hi[:, :, :off].abs().max()) == 0 and float(a_hi[:, L_out:].abs().max()) == 0   # nothing written outside
+    assert int(flag.item()) == 0
+
+
+def test_fused_norm_epilogue_needs_a_whole_clip_per_tile():
+    """u1 at the BASELINE time axis has 4 x 176 = 704 accumulator columns per clip: no fused norm (the ISTFT applies it)."""
+    from phasegen import ops
+    from phasegen._lib import PG_EPI_ACT, PG_EPI_NORM_ACT
+    kind, k, s, p, cim, com = GEOM["u1"]
+    d = ops.conv_desc(kind, 4, 128 * cim, 128 * com, 349, k, s, p, 352, 128 * cim, ops.PG_PREC_F16X2)
+    assert not ops.conv_epilogue_supported(d, PG_EPI_NORM_ACT) and ops.conv_epilogue_supported(d, PG_EPI_ACT)
+    x = torch.zeros(4, 352, 128 * cim, device="cuda", dtype=torch.float16)
+    w = torch.zeros(k, 128 * com, 128 * cim, device="cuda", dtype=torch.float16)
+    o = torch.zeros(4, 696, 128 * com, device="cuda", dtype=torch.float16)
+    epi = ops.conv_epilogue(PG_EPI_NORM_ACT, ops.act_dst(o, o, 696 * 128 * com, 128 * com, 0, 5, 0.0))
+    with pytest.raises(RuntimeError, match="whole clip|accumulator columns"):
+        ops.conv_tc(d, x, x, w, None, None, None, epi)
+
+
+def test_fp16_range_guard_fires_in_every_writer():
+    """Values beyond 65504 written into fp16 operand planes set the sticky flag (bn_act, fused conv epilogue, input
+    transpose, weight cast); the same values into bf16 planes do not."""
+    from phasegen import ops
+    from phasegen._lib import PG_DT_BF16_SPLIT, PG_DT_F16_SPLIT, PG_EPI_ACT
+    B, L, Cn = 2, 16, 64
+    y = torch.randn(B, L, Cn, device="cuda"); y[1, 3, 5] = 1.0e5
+    for dt, pdt, want in ((PG_DT_F16_SPLIT, torch.float16, 1), (PG_DT_BF16_SPLIT, torch.bfloat16, 0)):
+        flag = torch.zeros(1, device="cuda", dtype=torch.int32)
+        hi = torch.zeros(B, L, Cn, device="cuda", dtype=pdt); lo = torch.zeros_like(hi)
+        ops.bn_act(y, B, L, Cn, L, Cn, None, False, ops.act_dst(hi, lo, L * Cn, Cn, 0, dt, 1.0, flag))
+        assert int(flag.item()) == want
+        flag.zero_()
+        ops.transpose(y.permute(0, 2, 1).contiguous(), dst_hi=hi, dst_lo=lo, dst_batch_stride=L * Cn, dst_ld=Cn, range_flag=flag)
+        assert int(flag.item()) == want
+        flag.zero_()
+        ops.cast_split(y, hi, lo, flag)
+        assert int(flag.item()) == want
+    # fused epilogue: a convolution whose output exceeds the fp16 range
+    kind, k, s, p, C_in, C_out, rows, x, w = _case("d4", 64, 31, 2, seed=7)
+    w = w * 3.0e4
+    hi, lo, _ = ops.pack_weight(w, kind, plane_dtype=torch.float16)
+    xh = x.half(); xl = (x - xh.float()).half()
+    d = ops.conv_desc(kind, 2, C_in, C_out, 31, k, s, p, rows, C_in, ops.PG_PREC_F16X3)
+    flag = torch.zeros(1, device="cuda", dtype=torch.int32)
+    o_hi = torch.zeros(2, 16, C_out, device="cuda", dtype=torch.float16); o_lo = torch.zeros_like(o_hi)
+    ops.conv_tc(d, xh, xl, hi, lo, None, None,
+                ops.conv_epilogue(PG_EPI_ACT, ops.act_dst(o_hi, o_lo, 16 * C_out, C_out, 0, PG_DT_F16_SPLIT, 0.0, flag)))
+    assert int(flag.item()) == 1

@@ -26,7 +26,7 @@ int check_launch(const char* what) {
 }  // namespace pg
 
 extern "C" const char* pg_last_error(void) { return pg::g_err; }
-extern "C" int pg_abi_version(void) { return 2; }
+extern "C" int pg_abi_version(void) { return 3; }
 
 extern "C" int pg_check_device(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0, n = 0;
@@ -66,5 +66,6 @@ extern "C" int pg_conv_tc_plan(const pg_conv_desc* d, int* out, int n_out) {
     const int v[16] = {p.n_tile, p.n_ntiles, p.nb, p.strip_rows, p.pair, p.merged, p.mgroups, p.acc_stages,
                        p.n_chunks, p.n_cotiles, p.OS, p.IS, p.n_taps[0], p.n_taps[1], p.n_groups[0], p.n_groups[1]};
     for (int i = 0; i < 16; ++i) out[i] = v[i];
+    if (n_out >= 17) out[16] = p.whole_clip;
     return PG_OK;
 }

@@ -36,6 +36,10 @@ struct ConvPlan {
                                 // (accumulator column pitch strip_rows per clip, the strip_rows - n_tile columns between clips
                                 // are junk); strip_rows is the full strip, a CTA pair splits the tile by clips
     int clip_group;             // tensor-core tile order: clips per L2-resident group (set by the launcher)
+    int whole_clip;             // tensor-core path: a tile holds ALL output positions of its nb clips for its 128/256 channels --
+                                // every phase x position tile ("part") side by side in the accumulator, part (phase, nt) of
+                                // clip c at column ((c*OS + phase)*n_ntiles + nt)*n_tile -- so per-clip norm statistics are
+                                // complete inside the CTA and the epilogue can normalise + activate + write operand planes
     int out_rows, out_ld;
     int n_groups[2], n_taps[2];
     ConvGroup groups[2][kMaxTaps];
@@ -183,7 +187,38 @@ static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
             }
         }
     }
-    p->acc_stages = (p->merged ? p->nb * p->strip_rows : p->nb * p->n_tile) <= 256 ? 2 : 1;
+    // Whole-clip tiles (requested for the fused per-clip norm epilogue): OS x n_ntiles parts of one clip in <= 512 columns.
+    // Merged tiles already hold whole clips when there is one phase; otherwise they are given up for this layer.
+    p->whole_clip = 0;
+    if (d->tc_whole_clip) {
+        const int parts = p->OS * p->n_ntiles;
+        if (p->merged && p->OS > 1) {                                 // re-plan without merging (short two-phase layers)
+            p->merged = 0; p->mgroups = 1; p->nb = 1;
+            p->strip_rows = (n_cta + max_shift + 7) / 8 * 8;
+        }
+        if (!p->merged) {
+            if (parts * p->n_tile > 512) { set_error("conv plan: a whole clip needs %d accumulator columns (> 512)", parts * p->n_tile); return PG_ERR_UNSUPPORTED; }
+            if (parts > 1) {
+                p->whole_clip = 1;
+                int nb = 1;
+                if (weight_bound && 2 * parts * p->n_tile <= 512) nb = 2;      // two clips per weight tile where the weight stream is the bound
+                if (nb > d->B) nb = d->B;
+                const int planes = (d->precision == PG_PREC_BF16X3 || d->precision == PG_PREC_F16X3 || d->precision == PG_PREC_F16X2) ? 2 : 1;
+                if (nb * p->n_ntiles * p->strip_rows * planes * 128 > 72 * 1024) nb = 1;
+                // two strip slots plus at least two weight slots must fit the 227 KB of shared memory
+                if (p->n_ntiles * p->strip_rows * planes * 128 > 80 * 1024) {
+                    set_error("conv plan: the %d strips of a whole clip (%d rows each) do not fit shared memory", p->n_ntiles, p->strip_rows);
+                    return PG_ERR_UNSUPPORTED;
+                }
+                p->nb = nb;
+            }
+        }
+    }
+    {
+        const int cols = p->merged ? p->nb * p->strip_rows : p->nb * p->n_tile * (p->whole_clip ? p->OS * p->n_ntiles : 1);
+        if (cols > 512) { set_error("conv plan: tile needs %d accumulator columns (> 512)", cols); return PG_ERR_UNSUPPORTED; }
+        p->acc_stages = cols <= 256 ? 2 : 1;
+    }
     p->clip_group = d->B;
     return PG_OK;
 }

@@ -52,6 +52,13 @@ struct ConvTcParams {
     int f16;                        // operand planes are fp16 (else bf16)
     int base_offset_mode;           // descriptor base-offset handling for shifted strips
     int a_mn;                       // weight planes are [k][C_in][C_out]: A is fed MN-major (data-gradient mode)
+    // fused epilogue (model.py:80-83,113): PG_EPI_RAW stores y (+ statistics records); PG_EPI_ACT applies the activation(s)
+    // and writes the consumers' operand planes; PG_EPI_NORM_ACT first normalises with the clip's own statistics
+    // (train-mode norm of a batch-1 call), which are complete inside the tile (plan.whole_clip or a one-part layer)
+    int epi_mode;
+    const float* gamma; const float* beta; float eps;
+    ActDst dst0, dst1;
+    float2* ss_out;                 // NORM_ACT: optional [B][C_out] (scale, shift) record of what was applied
 };
 // plan.pair = 1: tiles are 256 output channels wide and owned by a CTA pair; plan.strip_rows is then the
 // HALF strip each CTA loads (n_tile/2 + largest shift rows).
@@ -67,17 +74,21 @@ struct TileCoord { int co_tile, phase, b0, nt; };
 // the group's activations are read from HBM once and re-used from L2 by every slab.
 __device__ __forceinline__ int n_bundles(const ConvPlan& p) { return (p.B + p.nb - 1) / p.nb; }
 __device__ __forceinline__ int n_co_slabs(const ConvPlan& p) { return p.pair ? p.n_cotiles / 2 : p.n_cotiles; }
-__device__ __forceinline__ int total_tiles(const ConvPlan& p) { return n_co_slabs(p) * p.OS * n_bundles(p) * p.n_ntiles; }
+// whole-clip tiles carry every phase and position tile of their clips: the phase / position-tile coordinates collapse
+__device__ __forceinline__ int tile_OS(const ConvPlan& p) { return p.whole_clip ? 1 : p.OS; }
+__device__ __forceinline__ int tile_NT(const ConvPlan& p) { return p.whole_clip ? 1 : p.n_ntiles; }
+__device__ __forceinline__ int total_tiles(const ConvPlan& p) { return n_co_slabs(p) * tile_OS(p) * n_bundles(p) * tile_NT(p); }
 __device__ __forceinline__ TileCoord decode_tile(const ConvPlan& p, int tile) {
     TileCoord c;
-    const int nbg = n_bundles(p), G = p.clip_group, n_slabs = n_co_slabs(p) * p.OS;
-    const int tiles_full = n_slabs * G * p.n_ntiles;
+    const int OSx = tile_OS(p), NTx = tile_NT(p);
+    const int nbg = n_bundles(p), G = p.clip_group, n_slabs = n_co_slabs(p) * OSx;
+    const int tiles_full = n_slabs * G * NTx;
     const int g = tile / tiles_full, r = tile % tiles_full;
     int Gg = nbg - g * G; if (Gg > G) Gg = G;
-    const int per_slab = Gg * p.n_ntiles;
+    const int per_slab = Gg * NTx;
     const int slab = r / per_slab, r2 = r % per_slab;
-    c.co_tile = slab / p.OS; c.phase = slab % p.OS;
-    c.b0 = (g * G + r2 / p.n_ntiles) * p.nb; c.nt = r2 % p.n_ntiles;
+    c.co_tile = slab / OSx; c.phase = slab % OSx;
+    c.b0 = (g * G + r2 / NTx) * p.nb; c.nt = r2 % NTx;
     return c;
 }
 
@@ -132,7 +143,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
     const int half_n = pl.n_tile >> 1;                            // PAIR, not merged: positions each CTA supplies per clip
     const int nb_grp = pl.nb / pl.mgroups;                        // clips per MMA (merged) / per tile (mgroups = 1)
     const int nb_cta = (PAIR && pl.merged) ? nb_grp >> 1 : nb_grp;   // clips of one group whose strips this CTA loads
-    const int col_pitch = pl.merged ? pl.strip_rows : pl.n_tile;  // accumulator columns per clip
+    const int t_phases = pl.whole_clip ? pl.OS : 1;               // phases / position tiles ("parts") held by one tile
+    const int t_nts = pl.whole_clip ? pl.n_ntiles : 1;
+    const int n_sub = pl.merged ? pl.mgroups : t_nts;             // activation boxes per strip slot
 
     if (warp == 0) {
         // ===================================================================== TMA producer
@@ -151,26 +164,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                 if (PAIR) tc.co_tile = tc.co_tile * 2 + rank;
                 const int m0 = tc.nt * pl.n_tile + ((PAIR && !pl.merged) ? rank * half_n : 0);
                 const int clip0 = tc.b0 + ((PAIR && pl.merged) ? rank * nb_cta : 0);   // + g * nb_grp per merged group
-                const int ng = pl.n_groups[tc.phase];
                 for (int ch = 0; ch < pl.n_chunks; ++ch) {
+                  for (int ph = tc.phase; ph < tc.phase + t_phases; ++ph) {
+                    const int ng = pl.n_groups[ph];
                     for (int g = 0; g < ng; ++g) {
-                        const ConvGroup grp = pl.groups[tc.phase][g];
+                        const ConvGroup grp = pl.groups[ph][g];
                         {
-                            const int s = b_it & 1; const uint32_t ph = (b_it >> 1) & 1;
-                            mbar_wait(emptyB + s, ph ^ 1);
+                            const int s = b_it & 1; const uint32_t bph = (b_it >> 1) & 1;
+                            mbar_wait(emptyB + s, bph ^ 1);
                             uint8_t* dst = b_base + (size_t)s * b_planes * bPlane;
                             if (elect_one()) {
                                 if (PAIR) { if (rank == 0) mbar_expect_tx(fullB + s, 2 * b_bytes); }   // both CTAs' halves
                                 else mbar_expect_tx(fullB + s, b_bytes);
-                                for (int mg = 0; mg < pl.mgroups; ++mg) {      // one box per merged group (its clips are contiguous)
-                                    uint8_t* dg = dst + (size_t)mg * grp_bytes;
-                                    const int cg = clip0 + mg * nb_grp;
+                                // one box per merged group (its clips are contiguous) / per position tile of a whole-clip tile
+                                for (int sub = 0; sub < n_sub; ++sub) {
+                                    uint8_t* dg = dst + (size_t)sub * grp_bytes;
+                                    const int cg = clip0 + (pl.merged ? sub * nb_grp : 0);
+                                    const int r0 = m0 + (pl.merged ? 0 : sub * pl.n_tile) + grp.row0;
                                     if (PAIR) {
-                                        tma_load_4d_pair(dg, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
-                                        if (x_lo) tma_load_4d_pair(dg + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
+                                        tma_load_4d_pair(dg, &map_x_hi, fullB + s, ch * 64, grp.parity, r0, cg);
+                                        if (x_lo) tma_load_4d_pair(dg + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, r0, cg);
                                     } else {
-                                        tma_load_4d(dg, &map_x_hi, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
-                                        if (x_lo) tma_load_4d(dg + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, m0 + grp.row0, cg);
+                                        tma_load_4d(dg, &map_x_hi, fullB + s, ch * 64, grp.parity, r0, cg);
+                                        if (x_lo) tma_load_4d(dg + bPlane, &map_x_lo, fullB + s, ch * 64, grp.parity, r0, cg);
                                     }
                                 }
                             }
@@ -178,9 +194,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                             ++b_it;
                         }
                         for (int j = 0; j < grp.n_taps; ++j) {
-                            const int w_idx = pl.taps[tc.phase][grp.first_tap + j].w_idx;
-                            const int s = a_slot; const uint32_t ph = a_ph;
-                            mbar_wait(emptyA + s, ph ^ 1);
+                            const int w_idx = pl.taps[ph][grp.first_tap + j].w_idx;
+                            const int s = a_slot; const uint32_t aph = a_ph;
+                            mbar_wait(emptyA + s, aph ^ 1);
                             uint8_t* dst = a_base + (size_t)s * a_planes * kATileBytes;
                             if (elect_one()) {
                                 if (!PAIR) mbar_expect_tx(fullA + s, a_bytes);
@@ -203,6 +219,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                             if (++a_slot == nA) { a_slot = 0; a_ph ^= 1; }
                         }
                     }
+                  }
                 }
             }
         }
@@ -215,7 +232,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
             int a_slot = 0; uint32_t a_ph = 0;
             // operand format field: 1 = bf16, 0 = fp16 (bits [7,10) for A, [10,13) for B)
             const int n_mma = pl.merged ? nb_grp * pl.strip_rows : pl.n_tile;
-            const int n_loop = pl.merged ? pl.mgroups : pl.nb;    // merged: one MMA covers every clip of a group
+            const int n_loop = pl.merged ? pl.mgroups : pl.nb * t_nts;    // merged: one MMA covers every clip of a group
             const uint32_t idesc = (make_idesc_bf16(n_mma, PAIR ? 256 : 128) & ~(prm.f16 ? ((7u << 7) | (7u << 10)) : 0u)) |
                                    (prm.a_mn ? (1u << 15) : 0u);
             const bool a_mn = prm.a_mn != 0;
@@ -233,30 +250,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                 mbar_wait_sleep(accEmpty + acc, acc_ph ^ 1, 200);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
-                const int ng = pl.n_groups[tc.phase];
-                uint32_t accumulate = 0, accumulate_rest = 0;
-                const uint32_t clip_bytes = pl.merged ? (uint32_t)nb_cta * pl.strip_rows * 128u : (uint32_t)pl.strip_rows * 128u;
-                const uint32_t col_step = pl.merged ? (uint32_t)n_mma : (uint32_t)pl.n_tile;
+                const uint32_t strip_bytes = (uint32_t)pl.strip_rows * 128u;
+                // merged: MMA c covers the nb_grp clips of group c (columns c*n_mma ...); else one MMA per (position tile,
+                // clip) of the tile, part (phase, nt) of clip c at column ((c*t_phases + phase)*t_nts + nt)*n_tile
+                const uint32_t clip_bytes = pl.merged ? (uint32_t)nb_cta * strip_bytes : strip_bytes;
                 for (int ch = 0; ch < pl.n_chunks; ++ch) {
+                  for (int ph = tc.phase; ph < tc.phase + t_phases; ++ph) {
+                    const int ng = pl.n_groups[ph];
+                    const int ph_sub = ph - tc.phase;
                     for (int g = 0; g < ng; ++g) {
-                        const ConvGroup grp = pl.groups[tc.phase][g];
+                        const ConvGroup grp = pl.groups[ph][g];
                         const int bs = b_it & 1; const uint32_t bph = (b_it >> 1) & 1;
                         mbar_wait(fullB + bs, bph);
                         tc_fence_after();
                         const uint32_t b_hi = smem_u32(b_base + (size_t)bs * b_planes * bPlane);
                         const uint32_t b_lo = b_hi + bPlane;
                         for (int j = 0; j < grp.n_taps; ++j) {
-                            const ConvTap tp = pl.taps[tc.phase][grp.first_tap + j];
+                            const ConvTap tp = pl.taps[ph][grp.first_tap + j];
                             const int as = a_slot; const uint32_t aph = a_ph;
                             mbar_wait(fullA + as, aph);
                             tc_fence_after();
                             const uint32_t a_hi = smem_u32(a_base + (size_t)as * a_planes * kATileBytes);
                             const uint32_t a_lo = a_hi + kATileBytes;
                             const uint32_t sh = (uint32_t)tp.shift * 128u;
-                            for (int c = 0; c < n_loop; ++c) {     // one MMA group per clip of the bundle
-                                const uint32_t boff = (uint32_t)c * clip_bytes + sh;
-                                const uint32_t dcol = d_tmem + c * col_step;
-                                const uint32_t acc_c = c == 0 ? accumulate : accumulate_rest;
+                            const uint32_t acc_first = (ch | g | j) ? 1u : 0u;   // first MMA into this phase's columns overwrites
+                            for (int c = 0; c < n_loop; ++c) {     // one MMA group per clip (x position tile) of the bundle
+                                uint32_t boff, dcol;
+                                if (pl.merged) {
+                                    boff = (uint32_t)c * clip_bytes + sh;
+                                    dcol = d_tmem + (uint32_t)c * (uint32_t)n_mma;
+                                } else {
+                                    const int nt_sub = c / pl.nb, cc = c - nt_sub * pl.nb;     // strips are laid out [nt][clip]
+                                    boff = (uint32_t)c * clip_bytes + sh;
+                                    dcol = d_tmem + (uint32_t)(((cc * t_phases + ph_sub) * t_nts + nt_sub) * pl.n_tile);
+                                }
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk) {   // 4 x (K = 16) per 64-channel chunk
                                     const uint64_t da_hi = a_mn ? make_desc_sw128_mn(a_hi + kk * 2048, 8192) : make_desc_sw128(a_hi + kk * 32, 0);
@@ -264,25 +291,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                                     if (w_lo) {
                                         const uint64_t da_lo = a_mn ? make_desc_sw128_mn(a_lo + kk * 2048, 8192) : make_desc_sw128(a_lo + kk * 32, 0);
                                         const uint64_t db_lo = make_desc_sw128(b_lo + boff + kk * 32, prm.base_offset_mode);
-                                        mma(dcol, da_lo, db_hi, kk == 0 ? acc_c : 1u);
+                                        mma(dcol, da_lo, db_hi, kk == 0 ? acc_first : 1u);
                                         mma(dcol, da_hi, db_lo, 1);
                                         mma(dcol, da_hi, db_hi, 1);
                                     } else if (x_lo) {
                                         const uint64_t db_lo = make_desc_sw128(b_lo + boff + kk * 32, prm.base_offset_mode);
-                                        mma(dcol, da_hi, db_lo, kk == 0 ? acc_c : 1u);
+                                        mma(dcol, da_hi, db_lo, kk == 0 ? acc_first : 1u);
                                         mma(dcol, da_hi, db_hi, 1);
                                     } else {
-                                        mma(dcol, da_hi, db_hi, kk == 0 ? acc_c : 1u);
+                                        mma(dcol, da_hi, db_hi, kk == 0 ? acc_first : 1u);
                                     }
                                 }
                             }
-                            accumulate = 1; accumulate_rest = 1;
                             commit(emptyA + as);
                             if (++a_slot == nA) { a_slot = 0; a_ph ^= 1; }
                         }
                         commit(emptyB + bs);
                         ++b_it;
                     }
+                  }
                 }
                 commit(accFull + acc);
             }
@@ -291,55 +318,123 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
         // ========================================================================= epilogue
         const int q = warp & 3;                               // TMEM lane quarter this warp may read
         uint32_t t_it = 0;
+        const int col_pitch = pl.merged ? pl.strip_rows : pl.n_tile * t_phases * t_nts;   // accumulator columns per clip
+        const int n_parts = t_phases * t_nts;
+        bool bad_range = false;
         for (int tile = tile0; tile < n_tiles; tile += tile_step, ++t_it) {
             TileCoord tc = decode_tile(pl, tile);
             if (PAIR) tc.co_tile = tc.co_tile * 2 + rank;
             const int acc = pl.acc_stages == 2 ? (t_it & 1) : 0;
             const uint32_t acc_ph = pl.acc_stages == 2 ? ((t_it >> 1) & 1) : (t_it & 1);
-            const int m0 = tc.nt * pl.n_tile;
-            const int l_phase = (pl.L_out - tc.phase + pl.OS - 1) / pl.OS;   // positions of this phase
-            int n_valid = l_phase - m0; if (n_valid > pl.n_tile) n_valid = pl.n_tile; if (n_valid < 0) n_valid = 0;
             mbar_wait_sleep(accFull + acc, acc_ph, 1000);
             tc_fence_after();
             const int co = tc.co_tile * 128 + q * 32 + lane;
+            // part p = (phase, position tile) of the tile: its valid columns and the output row of its column 0
+            auto part_geom = [&](int p, int& phase, int& m0, int& n_valid) {
+                phase = tc.phase + p / t_nts;
+                m0 = (tc.nt + p % t_nts) * pl.n_tile;
+                const int l_phase = (pl.L_out - phase + pl.OS - 1) / pl.OS;   // positions of this phase
+                n_valid = l_phase - m0; if (n_valid > pl.n_tile) n_valid = pl.n_tile; if (n_valid < 0) n_valid = 0;
+            };
             for (int c = 0; c < pl.nb; ++c) {
                 const int b = tc.b0 + c;
                 if (b >= pl.B) break;
-                const uint32_t taddr = tmem_base + acc * 256 + c * col_pitch + ((uint32_t)(q * 32) << 16);
-                // pass 1: mean over the valid columns
-                float sum = 0.f;
-                for (int c0 = 0; c0 < n_valid; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(taddr + c0, v);
+                const uint32_t tclip = tmem_base + acc * 256 + c * col_pitch + ((uint32_t)(q * 32) << 16);
+                if (prm.epi_mode == PG_EPI_RAW) {
+                    for (int p = 0; p < n_parts; ++p) {
+                        int phase, m0, n_valid;
+                        part_geom(p, phase, m0, n_valid);
+                        const uint32_t taddr = tclip + p * pl.n_tile;
+                        // pass 1: mean over the valid columns
+                        float sum = 0.f;
+                        for (int c0 = 0; c0 < n_valid; c0 += 16) {
+                            float v[16];
+                            tmem_ld16(taddr + c0, v);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) if (c0 + i < n_valid) sum += v[i];
-                }
-                const float mean = n_valid > 0 ? sum / (float)n_valid : 0.f;
-                // pass 2: centred second moment + store
-                float m2 = 0.f;
-                float* yrow = prm.y + ((size_t)b * pl.out_rows) * pl.out_ld + co;
-                for (int c0 = 0; c0 < n_valid; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(taddr + c0, v);
+                            for (int i = 0; i < 16; ++i) if (c0 + i < n_valid) sum += v[i];
+                        }
+                        const float mean = n_valid > 0 ? sum / (float)n_valid : 0.f;
+                        // pass 2: centred second moment + store
+                        float m2 = 0.f;
+                        float* yrow = prm.y + ((size_t)b * pl.out_rows) * pl.out_ld + co;
+                        for (int c0 = 0; c0 < n_valid; c0 += 16) {
+                            float v[16];
+                            tmem_ld16(taddr + c0, v);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (c0 + i < n_valid) {
-                            float d = v[i] - mean;
-                            m2 += d * d;
-                            const int row = (m0 + c0 + i) * pl.OS + tc.phase;
-                            yrow[(size_t)row * pl.out_ld] = v[i];
+                            for (int i = 0; i < 16; ++i) {
+                                if (c0 + i < n_valid) {
+                                    float d = v[i] - mean;
+                                    m2 += d * d;
+                                    const int row = (m0 + c0 + i) * pl.OS + phase;
+                                    yrow[(size_t)row * pl.out_ld] = v[i];
+                                }
+                            }
+                        }
+                        if (prm.stats) {
+                            const int P = pl.OS * pl.n_ntiles;
+                            const int pi = phase * pl.n_ntiles + m0 / pl.n_tile;
+                            prm.stats[((size_t)b * P + pi) * pl.C_out + co] = make_float4((float)n_valid, mean, m2, 0.f);
                         }
                     }
-                }
-                if (prm.stats) {
-                    const int P = pl.OS * pl.n_ntiles;
-                    const int p = tc.phase * pl.n_ntiles + tc.nt;
-                    prm.stats[((size_t)b * P + p) * pl.C_out + co] = make_float4((float)n_valid, mean, m2, 0.f);
+                } else {
+                    // fused norm (per-clip statistics, complete inside this tile) + activation(s) + operand-plane store
+                    float sc = 1.f, sh = 0.f;
+                    if (prm.epi_mode == PG_EPI_NORM_ACT) {
+                        float sum = 0.f; int n_tot = 0;
+                        for (int p = 0; p < n_parts; ++p) {
+                            int phase, m0, n_valid;
+                            part_geom(p, phase, m0, n_valid);
+                            n_tot += n_valid;
+                            for (int c0 = 0; c0 < n_valid; c0 += 16) {
+                                float v[16];
+                                tmem_ld16(tclip + p * pl.n_tile + c0, v);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) if (c0 + i < n_valid) sum += v[i];
+                            }
+                        }
+                        const float mean = n_tot > 0 ? sum / (float)n_tot : 0.f;
+                        float m2 = 0.f;
+                        for (int p = 0; p < n_parts; ++p) {
+                            int phase, m0, n_valid;
+                            part_geom(p, phase, m0, n_valid);
+                            for (int c0 = 0; c0 < n_valid; c0 += 16) {
+                                float v[16];
+                                tmem_ld16(tclip + p * pl.n_tile + c0, v);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) if (c0 + i < n_valid) { const float d = v[i] - mean; m2 += d * d; }
+                            }
+                        }
+                        const float var = n_tot > 0 ? m2 / (float)n_tot : 0.f;
+                        sc = (prm.gamma ? __ldg(prm.gamma + co) : 1.f) * rsqrtf(var + prm.eps);
+                        sh = (prm.beta ? __ldg(prm.beta + co) : 0.f) - mean * sc;
+                        if (prm.ss_out) prm.ss_out[(size_t)b * pl.C_out + co] = make_float2(sc, sh);
+                    }
+                    for (int p = 0; p < n_parts; ++p) {
+                        int phase, m0, n_valid;
+                        part_geom(p, phase, m0, n_valid);
+                        for (int c0 = 0; c0 < n_valid; c0 += 16) {
+                            float v[16];
+                            tmem_ld16(tclip + p * pl.n_tile + c0, v);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                if (c0 + i < n_valid) {
+                                    const int row = (m0 + c0 + i) * pl.OS + phase;
+                                    const float h = fmaf(v[i], sc, sh);
+                                    if (prm.dst0.dtype) bad_range |= store_act1(prm.dst0, b, row, co, h);
+                                    if (prm.dst1.dtype) bad_range |= store_act1(prm.dst1, b, row, co, h);
+                                }
+                            }
+                        }
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if (PAIR) mbar_arrive_leader(accEmpty + acc); else mbar_arrive(accEmpty + acc); }
+        }
+        if (bad_range) {
+            if (prm.dst0.range_flag) atomicOr(prm.dst0.range_flag, 1);
+            else if (prm.dst1.range_flag) atomicOr(prm.dst1.range_flag, 1);
         }
     }
     tc_fence_before();
@@ -374,22 +469,42 @@ int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t
     return PG_OK;
 }
 
-static int g_sm_count = 0, g_max_smem = 0;
+// per device (a process may drive several GPUs)
 void device_limits(int* sm_count, int* max_smem) {
-    if (!g_sm_count) {
+    static int sm_dev[kMaxDevices] = {}, smem_dev[kMaxDevices] = {};
+    const int slot = current_device_slot();
+    if (!sm_dev[slot]) {
         int dev = 0; cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&sm_dev[slot], cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&smem_dev[slot], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     }
-    *sm_count = g_sm_count; *max_smem = g_max_smem;
+    *sm_count = sm_dev[slot]; *max_smem = smem_dev[slot];
 }
 
 }  // namespace pg
 
-extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi,
-                          const uint16_t* w_lo, float* y, float* stats, pg_stream stream) {
+// Can the tensor-core kernel run `mode` as its fused epilogue for this layer?  PG_EPI_NORM_ACT needs every output position
+// of a clip inside one tile (<= 512 accumulator columns).  Returns 1 / 0, or a negative error code.
+extern "C" int pg_conv_epilogue_supported(const pg_conv_desc* d, int mode) {
     using namespace pg;
-    PG_REQUIRE(d && x_hi && w_hi && y, "pg_conv_tc: null pointer");
+    PG_REQUIRE(d, "pg_conv_epilogue_supported: null descriptor");
+    if (mode == PG_EPI_RAW) return 1;
+    if (mode != PG_EPI_ACT && mode != PG_EPI_NORM_ACT) return 0;
+    if (d->precision == PG_PREC_FP32_SIMT || d->C_in % 64 || d->C_out % 128) return 0;
+    if (mode == PG_EPI_ACT) return 1;
+    pg_conv_desc dd = *d;
+    dd.tc_whole_clip = 1;
+    ConvPlan pl;
+    if (conv_plan_build(&dd, &pl) != PG_OK) return 0;
+    return (pl.whole_clip || (pl.OS == 1 && pl.n_ntiles == 1)) ? 1 : 0;
+}
+
+extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi,
+                          const uint16_t* w_lo, float* y, float* stats, const pg_conv_epilogue* epi, pg_stream stream) {
+    using namespace pg;
+    const int epi_mode = epi ? epi->mode : PG_EPI_RAW;
+    PG_REQUIRE(d && x_hi && w_hi && (y || epi_mode != PG_EPI_RAW), "pg_conv_tc: null pointer");
+    PG_REQUIRE(epi_mode == PG_EPI_RAW || epi_mode == PG_EPI_ACT || epi_mode == PG_EPI_NORM_ACT, "pg_conv_tc: bad epilogue mode %d", epi_mode);
     PG_REQUIRE(d->precision >= PG_PREC_BF16X3 && d->precision <= PG_PREC_F16, "pg_conv_tc: precision must be BF16X3, BF16, F16X3, F16X2 or F16");
     const int n_terms = (d->precision == PG_PREC_BF16X3 || d->precision == PG_PREC_F16X3) ? 3 : d->precision == PG_PREC_F16X2 ? 2 : 1;
     const bool three = n_terms == 3;
@@ -400,11 +515,24 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     ConvTcParams prm;
     pg_conv_desc d_local = *d;
     if (const char* e = getenv("PG_TC_PAIR")) d_local.tc_cta_pair = atoi(e);   // A/B hook: 1 = single CTAs, 2 = require pairs
+    d_local.tc_whole_clip = epi_mode == PG_EPI_NORM_ACT ? 1 : 0;              // the plan follows the epilogue
     d = &d_local;
     int rc = conv_plan_build(d, &prm.plan);
     if (rc != PG_OK) return rc;
     const ConvPlan& pl = prm.plan;
-    { int a_, b_; device_limits(&a_, &b_); }
+    prm.epi_mode = epi_mode; prm.gamma = nullptr; prm.beta = nullptr; prm.eps = 1e-5f; prm.ss_out = nullptr;
+    if ((rc = to_act_dst(nullptr, 0, &prm.dst0, "pg_conv_tc", "dst0")) != PG_OK) return rc;
+    prm.dst1 = prm.dst0;
+    if (epi_mode != PG_EPI_RAW) {
+        PG_REQUIRE(epi_mode != PG_EPI_NORM_ACT || pl.whole_clip || (pl.OS == 1 && pl.n_ntiles == 1),
+                   "pg_conv_tc: the fused per-clip norm needs a whole clip per tile (L_out %d does not fit 512 accumulator columns)", pl.L_out);
+        if ((rc = to_act_dst(&epi->dst0, d->C_out, &prm.dst0, "pg_conv_tc", "dst0")) != PG_OK) return rc;
+        if ((rc = to_act_dst(&epi->dst1, d->C_out, &prm.dst1, "pg_conv_tc", "dst1")) != PG_OK) return rc;
+        PG_REQUIRE(prm.dst0.dtype || prm.dst1.dtype, "pg_conv_tc: fused epilogue without a destination");
+        prm.gamma = epi->gamma; prm.beta = epi->beta; prm.eps = epi->eps; prm.ss_out = reinterpret_cast<float2*>(epi->scale_shift);
+    }
+    int g_sm_count, g_max_smem;
+    device_limits(&g_sm_count, &g_max_smem);
     prm.y = y; prm.stats = reinterpret_cast<float4*>(stats);
     prm.n_terms = n_terms;
     prm.f16 = (d->precision == PG_PREC_F16X3 || d->precision == PG_PREC_F16X2 || d->precision == PG_PREC_F16) ? 1 : 0;
@@ -412,7 +540,7 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     prm.a_mn = d->weights_mn_major ? 1 : 0;
     const int nb_grp = pl.nb / pl.mgroups;
     const int nb_cta = (pl.pair && pl.merged) ? nb_grp / 2 : nb_grp;
-    prm.b_slot_bytes = pl.mgroups * nb_cta * pl.strip_rows * 128;
+    prm.b_slot_bytes = (pl.merged ? pl.mgroups : (pl.whole_clip ? pl.n_ntiles : 1)) * nb_cta * pl.strip_rows * 128;
     const int a_planes = n_terms == 3 ? 2 : 1, b_planes = n_terms >= 2 ? 2 : 1;
     // merged tiles read up to 15 rows past the last strip (junk columns only): 2 KB of slack keeps that inside the allocation
     const int fixed = 2 * b_planes * prm.b_slot_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + (pl.merged ? 2048 : 0);
@@ -464,7 +592,7 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
         if (G > nbg) G = nbg;
         prm.plan.clip_group = G;
     }
-    const int n_tiles = (pair ? pl.n_cotiles / 2 : pl.n_cotiles) * pl.OS * ((pl.B + pl.nb - 1) / pl.nb) * pl.n_ntiles;
+    const int n_tiles = (pair ? pl.n_cotiles / 2 : pl.n_cotiles) * ((pl.B + pl.nb - 1) / pl.nb) * (pl.whole_clip ? 1 : pl.OS * pl.n_ntiles);
     int units = pair ? g_sm_count / 2 : g_sm_count;           // persistent CTAs (or CTA pairs: one per TPC)
     if (const char* e = getenv("PG_TC_MAX_CTAS")) {           // experiment hook: leave SMs free (e.g. for NCCL)
         const int cap = atoi(e);

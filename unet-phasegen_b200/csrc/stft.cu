@@ -38,7 +38,7 @@ template <int NC> struct FrameCfg {
     static constexpr int PL = padded_len2(NC);              // float2 elements of one frame buffer
     static constexpr size_t smem_stft() { return sizeof(float2) * (Radix<NC, false>::TOTAL + NC + (size_t)FC * PL); }
     static constexpr int RING = FC + 3;                     // windowed frames kept on chip: this iteration's + 3 of the last
-    static constexpr size_t smem_istft() { return sizeof(float2) * (Radix<NC, true>::TOTAL + NC + (size_t)RING * PL) + sizeof(float) * HOP; }
+    static constexpr size_t smem_istft() { return sizeof(float2) * (Radix<NC, true>::TOTAL + NC + (size_t)RING * PL + NC /*scale/shift table*/) + sizeof(float) * HOP; }
 };
 
 // the threads of one frame: lanes of a warp (TG <= 32) or two warps on a named barrier (TG = 64)
@@ -197,7 +197,8 @@ template <int NC, bool FAST>
 __global__ void __launch_bounds__(kStftThreads)
 istft_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int mode, int T,
              const float2* __restrict__ tw_g, float* __restrict__ wave,
-             unsigned* __restrict__ peak_bits, int* __restrict__ nonfinite, int blocks_per_cta) {
+             unsigned* __restrict__ peak_bits, int* __restrict__ nonfinite, int blocks_per_cta,
+             const float2* __restrict__ b_ss, int b_ss_stride) {
     using Cfg = FrameCfg<NC>;
     using R = Radix<NC, true>;
     constexpr int FC = Cfg::FC, HOP = Cfg::HOP;
@@ -206,6 +207,9 @@ istft_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int
     cpx* tabs = reinterpret_cast<cpx*>(wss_full + HOP);
     cpx* win = tabs + R::TOTAL;                             // synthesis Hann, (w[2m], w[2m+1])
     cpx* ring = win + NC;                                   // RING = FC + 3 windowed frames, slot = (frame - F0) mod RING
+    // optional affine map of the second plane, b <- b*scale + shift per (clip, bin): the train-mode norm that ends the
+    // U-Net (model.py:83,91) applied here, so the last layer's raw output is read once and never re-written
+    float2* ss_tab = reinterpret_cast<float2*>(ring + (size_t)Cfg::RING * Cfg::PL);   // [NC], only when b_ss
 
     const int tid = threadIdx.x;
     const cpx* twc = reinterpret_cast<const cpx*>(tw_g);
@@ -217,9 +221,10 @@ istft_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int
         for (int q = 0; q < 4; ++q) { const float wn = 0.5f - 0.5f * tw_g[q * HOP + i].x; acc += wn * wn; }
         wss_full[i] = acc;
     }
+    const int b = blockIdx.y;
+    if (b_ss) for (int m = tid; m < NC; m += kStftThreads) ss_tab[m] = __ldg(b_ss + (size_t)b * b_ss_stride + m);
     __syncthreads();
 
-    const int b = blockIdx.y;
     const int J0 = blockIdx.x * blocks_per_cta;             // output hop-blocks [J0, J1) of this CTA
     const int J1 = min(J0 + blocks_per_cta, T - 1);
     const int F0 = J0 - 1;                                  // first frame needed
@@ -255,7 +260,11 @@ istft_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int
         if (live) {
             cpx x[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = spec_value(ra[j], rb[j], FAST ? (int)PG_SPEC_POLAR_LOG : mode);
+            for (int j = 0; j < 16; ++j) {
+                float pb = rb[j];
+                if (b_ss) { const float2 ss = ss_tab[inv_bin<NC>(t, j) - 1]; pb = fmaf(pb, ss.x, ss.y); }
+                x[j] = spec_value(ra[j], pb, FAST ? (int)PG_SPEC_POLAR_LOG : mode);
+            }
             if (NC == 512) inv_fused_first_512(s, t, tabs, scale, x);
             else inv_pre_generic<NC>(s, t, tabs, scale, x);
         }
@@ -348,7 +357,7 @@ static int launch_stft(const float* wave, int B, int N, int T, const float* tw, 
 
 template <int NC>
 static int launch_istft(const float* a, const float* bq, int mode, int B, int T, const float* tw, float* wave,
-                        float* peak, int* nonfinite, cudaStream_t st) {
+                        float* peak, int* nonfinite, cudaStream_t st, const float* b_ss, int b_ss_stride) {
     using Cfg = FrameCfg<NC>;
     auto k = (mode == PG_SPEC_POLAR_LOG && bq) ? istft_kernel<NC, true> : istft_kernel<NC, false>;
     const size_t sm = Cfg::smem_istft();
@@ -363,7 +372,8 @@ static int launch_istft(const float* a, const float* bq, int mode, int B, int T,
     const int blocks_per_cta = 11 * Cfg::FC - 3;
     dim3 grid((T - 1 + blocks_per_cta - 1) / blocks_per_cta, B);
     k<<<grid, kStftThreads, sm, st>>>(a, bq, mode, T, reinterpret_cast<const float2*>(tw), wave,
-                                     reinterpret_cast<unsigned*>(peak), nonfinite, blocks_per_cta);
+                                     reinterpret_cast<unsigned*>(peak), nonfinite, blocks_per_cta,
+                                     reinterpret_cast<const float2*>(b_ss), b_ss_stride);
     return check_launch("istft_kernel");
 }
 
@@ -429,20 +439,23 @@ extern "C" int pg_stft_pairs(const float* wave, int B, int N, int n_fft, int hop
 }
 
 extern "C" int pg_istft(const float* in_a, const float* in_b, int mode, int B, int T, int n_fft, int hop,
-                        const float* twiddle, float* wave, float* peak, int* nonfinite, pg_stream stream) {
+                        const float* twiddle, float* wave, float* peak, int* nonfinite,
+                        const float* b_scale_shift, int b_ss_per_clip, pg_stream stream) {
     PG_REQUIRE(in_a && twiddle && wave && B > 0 && T > 1, "pg_istft: null pointer or empty input");
     PG_REQUIRE(hop * 4 == n_fft, "pg_istft: hop must be n_fft/4 (got n_fft=%d hop=%d)", n_fft, hop);
     PG_REQUIRE(mode >= PG_SPEC_POLAR_LOG && mode <= PG_SPEC_POLAR_MAG, "pg_istft: bad mode %d", mode);
     PG_REQUIRE(in_b || mode != PG_SPEC_CARTESIAN, "pg_istft: second plane missing");   // polar modes: NULL phase = zero phase
     PG_REQUIRE(B <= 65535, "pg_istft: batch too large for one launch");
+    PG_REQUIRE(!b_scale_shift || in_b, "pg_istft: scale/shift given without a second plane");
+    const int ss_stride = b_ss_per_clip ? n_fft / 2 : 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (peak) cudaMemsetAsync(peak, 0, sizeof(float) * B, st);
     if (nonfinite) cudaMemsetAsync(nonfinite, 0, sizeof(int) * B, st);
     switch (n_fft) {
-        case 256:  return pg::launch_istft<128>(in_a, in_b, mode, B, T, twiddle, wave, peak, nonfinite, st);
-        case 512:  return pg::launch_istft<256>(in_a, in_b, mode, B, T, twiddle, wave, peak, nonfinite, st);
-        case 1024: return pg::launch_istft<512>(in_a, in_b, mode, B, T, twiddle, wave, peak, nonfinite, st);
-        case 2048: return pg::launch_istft<1024>(in_a, in_b, mode, B, T, twiddle, wave, peak, nonfinite, st);
+        case 256:  return pg::launch_istft<128>(in_a, in_b, mode, B, T, twiddle, wave, peak, nonfinite, st, b_scale_shift, ss_stride);
+        case 512:  return pg::launch_istft<256>(in_a, in_b, mode, B, T, twiddle, wave, peak, nonfinite, st, b_scale_shift, ss_stride);
+        case 1024: return pg::launch_istft<512>(in_a, in_b, mode, B, T, twiddle, wave, peak, nonfinite, st, b_scale_shift, ss_stride);
+        case 2048: return pg::launch_istft<1024>(in_a, in_b, mode, B, T, twiddle, wave, peak, nonfinite, st, b_scale_shift, ss_stride);
     }
     pg::set_error("pg_istft: n_fft must be 256, 512, 1024 or 2048 (got %d)", n_fft);
     return PG_ERR_UNSUPPORTED;

@@ -96,25 +96,6 @@ __global__ void bn_finalize_kernel(const float4* __restrict__ stats, int B, int 
 }
 
 // ------------------------------------------------------------------------------- BN + act
-struct ActDst {
-    void* hi; void* lo; long long batch_stride; int ld; int ch_off; int dtype; float slope;
-};
-
-__device__ __forceinline__ void store_act4(const ActDst& d, int b, int l, int c, float4 v) {
-    v.x = leaky(v.x, d.slope); v.y = leaky(v.y, d.slope); v.z = leaky(v.z, d.slope); v.w = leaky(v.w, d.slope);
-    const size_t o = (size_t)b * d.batch_stride + (size_t)l * d.ld + d.ch_off + c;
-    if (d.dtype == PG_DT_F32) {
-        *reinterpret_cast<float4*>(static_cast<float*>(d.hi) + o) = v;
-    } else {
-        __align__(8) uint16_t h[4], lo[4];
-        const int fmt = fmt_of_dtype(d.dtype);
-        split16(v.x, fmt, h[0], lo[0]); split16(v.y, fmt, h[1], lo[1]);
-        split16(v.z, fmt, h[2], lo[2]); split16(v.w, fmt, h[3], lo[3]);
-        *reinterpret_cast<uint2*>(static_cast<uint16_t*>(d.hi) + o) = *reinterpret_cast<uint2*>(h);
-        if (d.dtype == PG_DT_BF16_SPLIT || d.dtype == PG_DT_F16_SPLIT) *reinterpret_cast<uint2*>(static_cast<uint16_t*>(d.lo) + o) = *reinterpret_cast<uint2*>(lo);
-    }
-}
-
 __global__ void __launch_bounds__(256)
 bn_act_kernel(const float* __restrict__ y, int L, int C, int rows, int ld, const float2* __restrict__ scale_shift,
               int per_clip, ActDst d0, ActDst d1) {
@@ -122,6 +103,7 @@ bn_act_kernel(const float* __restrict__ y, int L, int C, int rows, int ld, const
     const size_t total = (size_t)L * c4;
     const int b = blockIdx.y;
     const float2* ss = scale_shift ? scale_shift + (size_t)(per_clip ? b : 0) * C : nullptr;
+    bool bad0 = false, bad1 = false;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int l = (int)(i / c4), c = (int)(i % c4) * 4;
         float4 v = *reinterpret_cast<const float4*>(y + ((size_t)b * rows + l) * ld + c);
@@ -131,8 +113,24 @@ bn_act_kernel(const float* __restrict__ y, int L, int C, int rows, int ld, const
             v.x = fmaf(v.x, s01.x, s01.y); v.y = fmaf(v.y, s01.z, s01.w);
             v.z = fmaf(v.z, s23.x, s23.y); v.w = fmaf(v.w, s23.z, s23.w);
         }
-        if (d0.dtype) store_act4(d0, b, l, c, v);
-        if (d1.dtype) store_act4(d1, b, l, c, v);
+        if (d0.dtype) bad0 |= store_act4(d0, b, l, c, v);
+        if (d1.dtype) bad1 |= store_act4(d1, b, l, c, v);
+    }
+    if (bad0 && d0.range_flag) atomicOr(d0.range_flag, 1);
+    if (bad1 && d1.range_flag) atomicOr(d1.range_flag, 1);
+}
+
+// eval-mode norm (nn.BatchNorm with running statistics): scale = gamma / sqrt(running_var + eps), shift = beta - mean*scale
+__global__ void bn_from_running_kernel(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, int C, int G, float2* __restrict__ scale_shift,
+                                       float2* __restrict__ mean_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float sc = (gamma ? gamma[c] : 1.f) * rsqrtf(var[c] + eps);
+    const float sh = (beta ? beta[c] : 0.f) - mean[c] * sc;
+    for (int g = 0; g < G; ++g) {
+        scale_shift[(size_t)g * C + c] = make_float2(sc, sh);
+        if (mean_var) mean_var[(size_t)g * C + c] = make_float2(mean[c], var[c]);
     }
 }
 
@@ -158,21 +156,25 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int transposed, 
 
 // ------------------------------------------------------------------------------ cast/split
 __global__ void __launch_bounds__(256)
-cast_split_kernel(const float* __restrict__ src, size_t n4, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int fmt) {
+cast_split_kernel(const float* __restrict__ src, size_t n4, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int fmt, int* __restrict__ range_flag) {
+    bool bad = false;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const float4 v = reinterpret_cast<const float4*>(src)[i];
+        if (fmt == PG_FMT_F16) bad |= !f16_fits(v.x) || !f16_fits(v.y) || !f16_fits(v.z) || !f16_fits(v.w);
         __align__(8) uint16_t h[4], l[4];
         split16(v.x, fmt, h[0], l[0]); split16(v.y, fmt, h[1], l[1]); split16(v.z, fmt, h[2], l[2]); split16(v.w, fmt, h[3], l[3]);
         reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
         if (lo) reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
     }
+    if (bad && range_flag) atomicOr(range_flag, 1);
 }
 
 // ----------------------------------------------------------------------------- transpose
 __global__ void transpose_kernel(const float* __restrict__ src, int R, int S, long long src_batch_stride,
                                  float* __restrict__ dst, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
-                                 long long dst_batch_stride, int dst_ld, int fmt) {
+                                 long long dst_batch_stride, int dst_ld, int fmt, int* __restrict__ range_flag) {
     __shared__ float tile[32][33];
+    bool bad = false;
     const int b = blockIdx.z;
     const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     const float* sp = src + (size_t)b * src_batch_stride;
@@ -190,11 +192,13 @@ __global__ void transpose_kernel(const float* __restrict__ src, int R, int S, lo
             if (hi) {
                 uint16_t h, l;
                 split16(v, fmt, h, l);
+                if (fmt == PG_FMT_F16) bad |= !f16_fits(v);
                 hi[o] = h;
                 if (lo) lo[o] = l;
             }
         }
     }
+    if (bad && range_flag) atomicOr(range_flag, 1);
 }
 
 }  // namespace pg
@@ -234,24 +238,14 @@ extern "C" int pg_bn_finalize(const float* stats, int B, int P, int C, int per_c
     return check_launch("bn_finalize_kernel");
 }
 
-static int to_dst(const pg_act_dst* s, int C, ActDst* o, const char* which) {
-    o->dtype = 0; o->hi = o->lo = nullptr; o->batch_stride = 0; o->ld = 0; o->ch_off = 0; o->slope = 1.f;
-    if (!s || s->dtype == PG_DT_NONE) return PG_OK;
-    PG_REQUIRE(s->dtype >= PG_DT_F32 && s->dtype <= PG_DT_F16, "pg_bn_act: %s: bad dtype %d", which, s->dtype);
-    PG_REQUIRE(s->hi && ((s->dtype != PG_DT_BF16_SPLIT && s->dtype != PG_DT_F16_SPLIT) || s->lo), "pg_bn_act: %s: null plane", which);
-    PG_REQUIRE(s->ld % 4 == 0 && s->ch_off % 4 == 0 && s->batch_stride % 4 == 0 && s->ch_off + C <= s->ld, "pg_bn_act: %s: misaligned or too narrow destination", which);
-    o->hi = s->hi; o->lo = s->lo; o->batch_stride = s->batch_stride; o->ld = s->ld; o->ch_off = s->ch_off; o->dtype = s->dtype; o->slope = s->slope;
-    return PG_OK;
-}
-
 extern "C" int pg_bn_act(const float* y, int B, int L, int C, int rows, int ld, const float* scale_shift, int per_clip,
                          const pg_act_dst* dst0, const pg_act_dst* dst1, pg_stream stream) {
     PG_REQUIRE(y && B > 0 && L > 0 && C > 0 && B <= 65535, "pg_bn_act: bad arguments");
     PG_REQUIRE(C % 4 == 0 && ld % 4 == 0, "pg_bn_act: channel count and pitch must be multiples of 4");
     ActDst d0, d1;
     int rc;
-    if ((rc = to_dst(dst0, C, &d0, "dst0")) != PG_OK) return rc;
-    if ((rc = to_dst(dst1, C, &d1, "dst1")) != PG_OK) return rc;
+    if ((rc = to_act_dst(dst0, C, &d0, "pg_bn_act", "dst0")) != PG_OK) return rc;
+    if ((rc = to_act_dst(dst1, C, &d1, "pg_bn_act", "dst1")) != PG_OK) return rc;
     const size_t total = (size_t)L * (C / 4);
     int gx = (int)((total + 255) / 256); if (gx > 1024) gx = 1024;
     bn_act_kernel<<<dim3(gx, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -270,20 +264,28 @@ extern "C" int pg_pack_weight(const float* w, int kind, int C_in, int C_out, int
     return check_launch("pack_weight_kernel");
 }
 
-extern "C" int pg_cast_split(const float* src, int64_t n, uint16_t* hi, uint16_t* lo, int fmt, pg_stream stream) {
+extern "C" int pg_bn_from_running(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
+                                  float eps, int C, int G, float* scale_shift, float* mean_var, pg_stream stream) {
+    PG_REQUIRE(running_mean && running_var && scale_shift && C > 0 && G > 0, "pg_bn_from_running: bad arguments");
+    bn_from_running_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        running_mean, running_var, gamma, beta, eps, C, G, reinterpret_cast<float2*>(scale_shift), reinterpret_cast<float2*>(mean_var));
+    return check_launch("bn_from_running_kernel");
+}
+
+extern "C" int pg_cast_split(const float* src, int64_t n, uint16_t* hi, uint16_t* lo, int fmt, int* range_flag, pg_stream stream) {
     PG_REQUIRE(src && hi && n > 0 && n % 4 == 0, "pg_cast_split: bad arguments (n must be a multiple of 4)");
     PG_REQUIRE(fmt == PG_FMT_BF16 || fmt == PG_FMT_F16, "pg_cast_split: bad operand format %d", fmt);
     const size_t n4 = (size_t)n / 4;
     int gx = (int)((n4 + 255) / 256); if (gx > 148 * 32) gx = 148 * 32;
-    cast_split_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, n4, hi, lo, fmt);
+    cast_split_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, n4, hi, lo, fmt, range_flag);
     return check_launch("cast_split_kernel");
 }
 
 extern "C" int pg_transpose(const float* src, int B, int R, int S, int64_t src_batch_stride, float* dst, uint16_t* dst_hi,
-                            uint16_t* dst_lo, int64_t dst_batch_stride, int dst_ld, int fmt, pg_stream stream) {
+                            uint16_t* dst_lo, int64_t dst_batch_stride, int dst_ld, int fmt, int* range_flag, pg_stream stream) {
     PG_REQUIRE(src && (dst || dst_hi) && B > 0 && R > 0 && S > 0 && B <= 65535 && dst_ld >= R, "pg_transpose: bad arguments");
     dim3 grid((S + 31) / 32, (R + 31) / 32, B);
     transpose_kernel<<<grid, dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        src, R, S, src_batch_stride, dst, dst_hi, dst_lo, dst_batch_stride, dst_ld, fmt);
+        src, R, S, src_batch_stride, dst, dst_hi, dst_lo, dst_batch_stride, dst_ld, fmt, range_flag);
     return check_launch("transpose_kernel");
 }

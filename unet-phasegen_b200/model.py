@@ -10,8 +10,9 @@ What is kept from the reference interface
   * ``UNetBlock(outer_nc, inner_nc, k_size, stride, padding, input_nc, cat_nc, submodule, pos,
     norm_layer, transpose)`` with the same nesting, so ``model.state_dict()`` has exactly the
     reference's keys and shapes and reference checkpoints load.
-  * train-mode normalisation statistics on every call (the reference never calls ``.eval()``),
-    over (B, L) like train.py:42.  ``forward(x, per_clip=True)`` computes them per clip -- what
+  * train-mode normalisation statistics on every call while ``model.training`` (the reference never
+    calls ``.eval()``), over (B, L) like train.py:42; after ``model.eval()`` the running statistics are
+    used, as ``nn.BatchNorm`` does.  ``forward(x, per_clip=True)`` computes them per clip -- what
     the demo.py:33-42 batch-1 loop produces -- so a whole batch of clips can be inferred at once.
   * a time axis that breaks a skip concat raises RuntimeError, as torch.cat does at model.py:113.
 
@@ -117,7 +118,11 @@ class _UNetFunction(torch.autograd.Function):
         out_cl = ex.run(dn, up)
         if net.training:
             net._update_running_stats(ex)
-        ctx.net, ctx.ex, ctx.norms = net, ex, (dn, up)
+        # The executor (saved activations, raw conv outputs, statistics) is shared by every forward of this shape:
+        # stamp the run so that a backward whose forward state has been overwritten raises instead of returning
+        # gradients of the wrong graph.
+        ex.generation = getattr(ex, "generation", 0) + 1
+        ctx.net, ctx.ex, ctx.norms, ctx.generation = net, ex, (dn, up), ex.generation
         from phasegen import ops
         return ops.transpose(out_cl)
 
@@ -125,6 +130,11 @@ class _UNetFunction(torch.autograd.Function):
     def backward(ctx, grad_out):
         from phasegen import ops
         net, ex = ctx.net, ctx.ex
+        if ctx.generation != ex.generation:
+            raise RuntimeError(
+                "phasegen: backward() of a UNetModel forward whose saved state was overwritten by a later forward of the "
+                "same shape (one set of activation buffers per shape). Call backward() before the next forward of that "
+                "shape -- for gradient accumulation, accumulate p.grad across forward/backward pairs.")
         ops.transpose(grad_out.float().contiguous(), dst=ex.d_out)        # [B,2C,T] -> channels-last
         ex.backward(*ctx.norms)
         return (None, None) + tuple(net._param_grads(ex))
@@ -179,6 +189,8 @@ class UNetModel(nn.Module):
 
     def executor(self, B, T, device, per_clip=False, phase_only=None, **kw):
         levels = self._levels()
+        if not self.training and not per_clip:
+            kw.setdefault("use_running", True)      # nn.BatchNorm eval mode: normalise with the running statistics
         prec = kw.pop("precision", None) or self._resolve_precision(levels)
         phase_only = self.phase_only if phase_only is None else phase_only
         c_final = levels[0].up.C_out // 2 if phase_only else None
@@ -248,6 +260,28 @@ class UNetModel(nn.Module):
             ex.pack_weights(ws[:n], ws[n:])
             self._packed[id(ex)] = stamp
 
+    def invalidate_packed(self):
+        """Force every executor to re-pack its tensor-core weight planes on its next use.  Needed after writing
+        weights behind autograd's back (``p.data.copy_(...)``, ``weights_init``'s ``m.weight.data`` writes, EMA swaps):
+        such writes change neither ``data_ptr`` nor ``_version``, which is what the automatic check looks at."""
+        self._packed.clear()
+
+    def _running_stats(self):
+        """Per level (running_mean, running_var) of the down and up norms (None where there is no norm)."""
+        dn, up = [], []
+        for b in self._blocks():
+            for lst, m in ((dn, b._parts["down_norm"]), (up, b._parts["up_norm"])):
+                lst.append(None if m is None or getattr(m, "running_mean", None) is None else (m.running_mean, m.running_var))
+        return dn, up
+
+    def _run(self, ex, dn, up, **kw):
+        if ex.use_running:
+            rd, ru = self._running_stats()
+            if any(r is None for r in ru):
+                raise RuntimeError("phasegen: eval() needs norm layers that track running statistics")
+            kw.update(dn_running=rd, up_running=ru)
+        return ex.run(dn, up, **kw)
+
     def _mark_packed(self, ex):
         """Called by the native optimiser step: it changed the weights behind autograd's back and
         refreshed `ex`'s operand planes itself; every other executor must re-pack."""
@@ -300,7 +334,7 @@ class UNetModel(nn.Module):
             raise RuntimeError(f"expected {ex.levels[0].down.C_in} input channels, got {Cn}")
         ex.load_input_cf(x)
         dn, up = self._norm_params(x.device)
-        out_cl = ex.run(dn, up)                               # [B, T, C_final] channels-last
+        out_cl = self._run(ex, dn, up)                        # [B, T, C_final] channels-last
         if self.training and not per_clip and ex.C_final == ex.levels[0].up.C_out:
             self._update_running_stats(ex)
         from phasegen import ops
@@ -313,7 +347,7 @@ class UNetModel(nn.Module):
         ex = self.executor(B, T, x_cl.device, per_clip=per_clip, phase_only=phase_only)
         ex.load_input_cl(x_cl.contiguous())
         dn, up = self._norm_params(x_cl.device)
-        return ex.run(dn, up)
+        return self._run(ex, dn, up)
 
     def save(self, path):
         torch.save({k: v.detach().cpu() for k, v in self.model.state_dict().items()}, path)
@@ -331,11 +365,14 @@ class UNetModel(nn.Module):
             return _SaveHandle(None)
         cur = torch.cuda.current_stream(dev)
         side = self.__dict__.setdefault("_save_stream", torch.cuda.Stream(device=dev))
+        # Snapshot first: state_dict() aliases the LIVE parameters, and the next optimiser step would overwrite them
+        # while the (tens of ms long) device->host copy is still in flight.  The device-to-device clone is ordered on
+        # the training stream (1-2 ms at HBM speed for the 2.45 GB model); the host copy then reads the snapshot.
+        snap = {k: v.detach().clone() for k, v in sd.items()}
         side.wait_stream(cur)
         host = {}
         with torch.cuda.stream(side):
-            for k, v in sd.items():
-                src = v.detach()
+            for k, src in snap.items():
                 buf = torch.empty(src.shape, dtype=src.dtype, device="cpu", pin_memory=True)
                 buf.copy_(src, non_blocking=True)          # a strided (packed-storage) source lands contiguous
                 src.record_stream(side)

@@ -6,7 +6,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (ActDst, ConvDesc, PG_CONV, PG_CONV_TRANSPOSE, PG_DT_BF16, PG_DT_BF16_SPLIT, PG_DT_F16,
+from ._lib import (ActDst, ConvDesc, ConvEpilogue, PG_EPI_ACT, PG_EPI_NORM_ACT, PG_EPI_RAW, PG_CONV, PG_CONV_TRANSPOSE, PG_DT_BF16, PG_DT_BF16_SPLIT, PG_DT_F16,
                    PG_DT_F16_SPLIT, PG_DT_F32, PG_DT_NONE, PG_FMT_BF16, PG_FMT_F16, PG_PREC_BF16, PG_PREC_BF16X3,
                    PG_PREC_F16X2, PG_PREC_F16X3, PG_PREC_FP32_SIMT, PG_SPEC_CARTESIAN, PG_SPEC_POLAR_LOG,
                    PG_SPEC_POLAR_MAG, PG_STFT_LOGMAG, PG_STFT_REIM)
@@ -14,8 +14,10 @@ from ._lib import (ActDst, ConvDesc, PG_CONV, PG_CONV_TRANSPOSE, PG_DT_BF16, PG_
 SUPPORTED_N_FFT = (256, 512, 1024, 2048)
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(t=None):
+    """The current stream of the device `t` lives on (of the current device when no tensor is given)."""
+    dev = t.device if isinstance(t, torch.Tensor) and t.is_cuda else None
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 def _ptr(t):
@@ -36,6 +38,10 @@ def _need_cuda(t, name, dtype=torch.float32):
         raise RuntimeError(f"phasegen: `{name}` must be a CUDA tensor (there is no CPU path)")
     if t.dtype != dtype:
         raise RuntimeError(f"phasegen: `{name}` must be {dtype}, got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        # kernels are launched on the CURRENT device's stream: a tensor elsewhere would be read from the wrong device
+        raise RuntimeError(f"phasegen: `{name}` lives on {t.device} but the current device is cuda:{torch.cuda.current_device()}; "
+                           "wrap the call in `with torch.cuda.device(tensor.device):`")
     _lib.require_device(t.device.index)
     return t.contiguous()
 
@@ -108,9 +114,11 @@ def stft_pairs(wave, n_fft, hop, mean=0.0, std=1.0):
     return lm, ph
 
 
-def istft(a, b, mode, n_fft, hop, normalize=True, check_finite=True, out=None):
+def istft(a, b, mode, n_fft, hop, normalize=True, check_finite=True, out=None, b_scale_shift=None, bad_out=None):
     """(a, b) fp32 [B,T,n_fft/2] frame-major -> wave [B,(T-1)*hop]; optional peak normalisation
-    (utils.py:42) and finiteness check (utils.py:41; costs one device->host sync)."""
+    (utils.py:42) and finiteness check (utils.py:41; costs one device->host sync).
+    b_scale_shift: float2 per bin, [B, C, 2] (per clip) or [1, C, 2] / [C, 2]: b is read as b*scale + shift (the final
+    norm of the U-Net applied on the fly).  bad_out: int32 [B] buffer that receives the per-clip non-finite flags."""
     check_stft_geometry(n_fft, hop)
     a = _need_cuda(a, "a")
     b = _need_cuda(b, "b") if b is not None else None
@@ -122,9 +130,15 @@ def istft(a, b, mode, n_fft, hop, normalize=True, check_finite=True, out=None):
         raise RuntimeError(f"phasegen.istft: `out` must be a contiguous CUDA float32 [{B}, {n}] tensor")
     wave = out if out is not None else torch.empty(B, n, device=a.device, dtype=torch.float32)
     peak = torch.empty(B, device=a.device, dtype=torch.float32)
-    bad = torch.empty(B, device=a.device, dtype=torch.int32)
+    bad = bad_out if bad_out is not None else torch.empty(B, device=a.device, dtype=torch.int32)
+    per_clip = 0
+    if b_scale_shift is not None:
+        b_scale_shift = _need_cuda(b_scale_shift, "b_scale_shift")
+        if b_scale_shift.numel() not in (2 * Cb, 2 * Cb * B):
+            raise RuntimeError("phasegen.istft: b_scale_shift must hold (scale, shift) per bin, for all clips or per clip")
+        per_clip = int(b_scale_shift.numel() == 2 * Cb * B and B > 1)
     _lib.call("pg_istft", _ptr(a), _ptr(b), mode, B, T, n_fft, hop, _ptr(twiddle(n_fft, a.device)),
-              _ptr(wave), _ptr(peak), _ptr(bad), _stream())
+              _ptr(wave), _ptr(peak), _ptr(bad), _ptr(b_scale_shift), per_clip, _stream())
     if normalize:
         _lib.call("pg_peak_normalize", _ptr(wave), _ptr(peak), B, n, _stream())
     if check_finite and bool(bad.any().item()):
@@ -132,7 +146,7 @@ def istft(a, b, mode, n_fft, hop, normalize=True, check_finite=True, out=None):
     return wave, peak
 
 
-def transpose(src, dst=None, dst_hi=None, dst_lo=None, dst_batch_stride=None, dst_ld=None):
+def transpose(src, dst=None, dst_hi=None, dst_lo=None, dst_batch_stride=None, dst_ld=None, range_flag=None):
     """[B,R,S] fp32 -> [B,S,R] (fp32 and/or bf16 hi/lo planes with the given pitch)."""
     src = _need_cuda(src, "src")
     B, R, S = src.shape
@@ -140,17 +154,18 @@ def transpose(src, dst=None, dst_hi=None, dst_lo=None, dst_batch_stride=None, ds
         dst = torch.empty(B, S, R, device=src.device, dtype=torch.float32)
     ld = R if dst_ld is None else dst_ld
     bs = S * ld if dst_batch_stride is None else dst_batch_stride
-    _lib.call("pg_transpose", _ptr(src), B, R, S, R * S, _ptr(dst), _ptr(dst_hi), _ptr(dst_lo), bs, ld, _fmt(dst_hi), _stream())
+    _lib.call("pg_transpose", _ptr(src), B, R, S, R * S, _ptr(dst), _ptr(dst_hi), _ptr(dst_lo), bs, ld, _fmt(dst_hi), _ptr(range_flag), _stream())
     return dst
 
 
 def conv_desc(kind, B, C_in, C_out, L_in, k, stride, pad, in_rows, in_ld, precision, L_out=None,
-              out_rows=None, out_ld=None, taps_per_group=0, base_offset_mode=0, max_ctas=0, max_clips_per_tile=0, weights_mn_major=0, cta_pair=0):
+              out_rows=None, out_ld=None, taps_per_group=0, base_offset_mode=0, max_ctas=0, max_clips_per_tile=0, weights_mn_major=0, cta_pair=0,
+              whole_clip=0):
     if L_out is None:
         L_out = (L_in - 1) * stride - 2 * pad + k if kind == PG_CONV_TRANSPOSE else (L_in + 2 * pad - k) // stride + 1
     return ConvDesc(kind, B, C_in, C_out, L_in, L_out, k, stride, pad, in_rows, in_ld,
                     L_out if out_rows is None else out_rows, C_out if out_ld is None else out_ld,
-                    precision, taps_per_group, base_offset_mode, max_ctas, max_clips_per_tile, weights_mn_major, cta_pair)
+                    precision, taps_per_group, base_offset_mode, max_ctas, max_clips_per_tile, weights_mn_major, cta_pair, whole_clip)
 
 
 def pack_weight(w, kind, want_tc=True, want_simt=False, plane_dtype=torch.bfloat16, want_lo=True):
@@ -170,8 +185,27 @@ def pack_weight(w, kind, want_tc=True, want_simt=False, plane_dtype=torch.bfloat
     return hi, lo, simt
 
 
-def conv_tc(desc, x_hi, x_lo, w_hi, w_lo, y, stats):
-    _lib.call("pg_conv_tc", C.byref(desc), _ptr(x_hi), _ptr(x_lo), _ptr(w_hi), _ptr(w_lo), _ptr(y), _ptr(stats), _stream())
+def conv_tc(desc, x_hi, x_lo, w_hi, w_lo, y, stats, epilogue=None):
+    """epilogue: a ConvEpilogue (conv_epilogue()) to fuse activation / per-clip norm + activation and the operand-plane
+    writes into the kernel; None = raw fp32 output + statistics records."""
+    _lib.call("pg_conv_tc", C.byref(desc), _ptr(x_hi), _ptr(x_lo), _ptr(w_hi), _ptr(w_lo), _ptr(y), _ptr(stats),
+              C.byref(epilogue) if epilogue is not None else None, _stream())
+
+
+_NO_DST = ActDst(None, None, 0, 0, 0, PG_DT_NONE, 1.0, None)
+
+
+def conv_epilogue(mode, dst0, dst1=None, gamma=None, beta=None, eps=1e-5, scale_shift=None):
+    return ConvEpilogue(mode, gamma.data_ptr() if gamma is not None else None, beta.data_ptr() if beta is not None else None,
+                        float(eps), dst0, dst1 if dst1 is not None else _NO_DST,
+                        scale_shift.data_ptr() if scale_shift is not None else None)
+
+
+def conv_epilogue_supported(desc, mode):
+    r = _lib.load().pg_conv_epilogue_supported(C.byref(desc), mode)
+    if r < 0:
+        raise RuntimeError(f"pg_conv_epilogue_supported failed ({r}): {_lib.last_error()}")
+    return bool(r)
 
 
 def conv_stat_parts(desc):
@@ -194,9 +228,16 @@ def bn_finalize(stats, B, P, Cn, per_clip, gamma, beta, eps, scale_shift, mean_v
               _ptr(scale_shift), _ptr(mean_var), _stream())
 
 
-def act_dst(hi, lo, batch_stride, ld, ch_off, dtype, slope):
+def act_dst(hi, lo, batch_stride, ld, ch_off, dtype, slope, range_flag=None):
     return ActDst(hi.data_ptr() if hi is not None else None, lo.data_ptr() if lo is not None else None,
-                  batch_stride, ld, ch_off, dtype, slope)
+                  batch_stride, ld, ch_off, dtype, slope, range_flag.data_ptr() if range_flag is not None else None)
+
+
+def bn_from_running(running_mean, running_var, gamma, beta, eps, scale_shift, mean_var=None):
+    """eval-mode norm: (scale, shift) from the running statistics, replicated over the G rows of scale_shift [G, C, 2]."""
+    G, Cn = scale_shift.shape[0], scale_shift.shape[1]
+    _lib.call("pg_bn_from_running", _ptr(running_mean), _ptr(running_var), _ptr(gamma), _ptr(beta), float(eps), Cn, G,
+              _ptr(scale_shift), _ptr(mean_var), _stream())
 
 
 def bn_act(y, B, L, Cn, rows, ld, scale_shift, per_clip, dst0, dst1=None):
@@ -243,9 +284,9 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0, w_hi=None
               _ptr(w_hi), _ptr(w_lo), _stream())
 
 
-def cast_split(src, hi, lo=None):
+def cast_split(src, hi, lo=None, range_flag=None):
     """fp32 (contiguous) -> bf16 or fp16 hi(/lo) planes of the same element order."""
-    _lib.call("pg_cast_split", _ptr(src), src.numel(), _ptr(hi), _ptr(lo), _fmt(hi), _stream())
+    _lib.call("pg_cast_split", _ptr(src), src.numel(), _ptr(hi), _ptr(lo), _fmt(hi), _ptr(range_flag), _stream())
 
 
 def packed_view(weight, kind):

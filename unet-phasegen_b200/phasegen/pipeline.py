@@ -8,7 +8,7 @@ numpy/CPU round trips the reference makes at demo.py:37-40.
 import torch
 
 from . import ops
-from ._lib import PG_DT_F32, PG_SPEC_POLAR_LOG, PG_STFT_LOGMAG
+from ._lib import PG_DT_F32, PG_PREC_FP32_SIMT, PG_SPEC_POLAR_LOG, PG_STFT_LOGMAG
 
 
 class _GraphedPipeline:
@@ -24,23 +24,35 @@ class _GraphedPipeline:
 
 
 class PhaseGenPipeline:
-    def __init__(self, model, n_fft, hop, precision=None, per_clip=True, phase_only=True, normalize=True):
+    def __init__(self, model, n_fft, hop, precision=None, per_clip=True, phase_only=True, normalize=True,
+                 fp16_overflow="raise"):
+        """fp16_overflow: what a checked call (check_finite=True) does when an activation left the fp16 range in one
+        of the fp16 operand modes: "raise" (OverflowError) or "fallback" (re-run the batch with precision="bf16x3":
+        bf16 planes have the fp32 range).  Unchecked calls leave the sticky flag for `range_overflow()`."""
         ops.check_stft_geometry(n_fft, hop)
+        if fp16_overflow not in ("raise", "fallback"):
+            raise ValueError("fp16_overflow must be 'raise' or 'fallback'")
         self.model, self.n_fft, self.hop = model, n_fft, hop
         self.per_clip, self.phase_only, self.normalize = per_clip, phase_only, normalize
-        self.precision = precision
+        self.precision, self.fp16_overflow = precision, fp16_overflow
+        self._executors = []
+        self._bad = None
 
     def frames(self, n_samples):
         return 1 + n_samples // self.hop
 
-    def __call__(self, wave, check_finite=False, return_intermediates=False, wave_out=None):
-        """wave float32 [B, N] on the GPU, N = (T-1)*hop with T % 8 == 0 -> float32 [B, N]."""
+    def __call__(self, wave, check_finite=False, return_intermediates=False, wave_out=None, _precision=None):
+        """wave float32 [B, N] on the GPU, N = (T-1)*hop with T % 8 == 0 -> float32 [B, N].
+        check_finite=True is the finiteness check of utils.py:41 plus the fp16-range guard (one device->host sync)."""
         if not wave.is_cuda:
             raise RuntimeError("PhaseGenPipeline needs CUDA tensors: there is no CPU fallback")
         B, N = wave.shape
         T = self.frames(N)
-        kw = {"precision": self.precision} if self.precision else {}
+        prec = _precision or self.precision
+        kw = {"precision": prec} if prec else {}
         ex = self.model.executor(B, T, wave.device, per_clip=self.per_clip, phase_only=self.phase_only, **kw)
+        if not any(e is ex for e in self._executors):
+            self._executors = (self._executors + [ex])[-8:]
         x0 = ex.x0
         if x0.dtype != PG_DT_F32:
             # the STFT kernel writes the first convolution's 16-bit operand planes directly
@@ -50,14 +62,47 @@ class PhaseGenPipeline:
             logmag, _ = ops.stft(wave, self.n_fft, self.hop, PG_STFT_LOGMAG, want_second=False)
             ex.load_input_cl(logmag)
         dn, up = self.model._norm_params(wave.device)
-        out = ex.run(dn, up)                                   # [B, T, C] phase (or [B, T, 2C])
         C = self.n_fft // 2
-        phase = out if out.shape[2] == C else out[:, :, :C].contiguous()
-        audio, peak = ops.istft(logmag, phase, PG_SPEC_POLAR_LOG, self.n_fft, self.hop,
-                                normalize=self.normalize, check_finite=check_finite, out=wave_out)
+        ss = None
+        if ex.C_final == C:
+            # the last norm is applied by the ISTFT kernel while it reads the raw phase plane (no normalising pass)
+            phase, ss = self.model._run(ex, dn, up, defer_last=True)
+        else:
+            phase = self.model._run(ex, dn, up)[:, :, :C].contiguous()      # [B, T, 2C] -> phase half
+        if self._bad is None or self._bad.shape[0] < B or self._bad.device != wave.device:
+            self._bad = torch.zeros(max(B, 256), device=wave.device, dtype=torch.int32)
+        audio, peak = ops.istft(logmag, phase, PG_SPEC_POLAR_LOG, self.n_fft, self.hop, normalize=self.normalize,
+                                check_finite=False, out=wave_out, b_scale_shift=ss, bad_out=self._bad[:B])
+        if check_finite:
+            try:
+                ex.check_range()
+            except OverflowError:
+                if self.fp16_overflow == "fallback" and _precision is None:
+                    return self(wave, check_finite, return_intermediates, wave_out, _precision="bf16x3")
+                raise
+            if bool(self._bad[:B].any().item()):
+                raise ValueError("Audio buffer is not finite everywhere")
         if return_intermediates:
+            if ss is not None:                                  # the normalised phase, materialised for inspection only
+                phase_n = torch.empty_like(phase)
+                ops.bn_act(phase, B, T, C, T, C, ss, self.per_clip, ops.act_dst(phase_n, None, T * C, C, 0, PG_DT_F32, 1.0))
+                phase = phase_n
             return audio, logmag, phase
         return audio
+
+    def range_overflow(self):
+        """Sticky fp16-range flags of every executor this pipeline has used, read and cleared (one small device->host
+        read per executor): True means some activation left the fp16 range since the last call."""
+        hit = False
+        for ex in self._executors:
+            if int(ex.range_flag.item()):
+                ex.range_flag.zero_()
+                hit = True
+        return hit
+
+    def nonfinite_clips(self, B):
+        """Per-clip non-finite flags of the LAST call (utils.py:41), as a host list."""
+        return [] if self._bad is None else [i for i, v in enumerate(self._bad[:B].tolist()) if v]
 
     def capture(self, B, n_samples, device=None, warmup=2):
         """CUDA-graph form of the pipeline for one fixed shape: the ~25 launches of a call are recorded once and
