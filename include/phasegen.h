@@ -75,6 +75,15 @@ int pg_istft(const float* in_a, const float* in_b, int mode, int B, int T, int n
              const float* b_scale_shift, int b_ss_per_clip, pg_stream stream);
 int pg_peak_normalize(float* wave, const float* peak, int B, int N, pg_stream stream);
 
+/* Long-form stitching (BASELINE.json config 4; the reference cuts long audio into independent slices,
+ * preproc_mdb.py:66-82, and never stitches them): n_windows windows of `win` samples, one every `step` samples
+ * (win/2 <= step <= win), cross-faded over the shared samples with complementary periodic-Hann ramps -> out [n_out].
+ * Window i is read from slot (i % world) * per_rank + i / world of `windows` [world * per_rank][win]: the layout an
+ * all-gather of round-robin-dealt windows produces (world = 1, per_rank = n_windows: plain order).  peak (may be NULL):
+ * one float, max |out|, for a single pg_peak_normalize(out, peak, 1, n_out) of the whole recording. */
+int pg_stitch(const float* windows, int n_windows, int win, int step, int world, int per_rank, float* out,
+              int64_t n_out, float* peak, pg_stream stream);
+
 /* ---------------------------------------------------------------- U-Net layers
  * Replace the nn.Conv1d / nn.ConvTranspose1d / norm / activation / torch.cat calls of
  * model.py:77-113.  A layer is: convolution -> per-channel statistics records -> finalize

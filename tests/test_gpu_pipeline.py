@@ -245,3 +245,37 @@ def test_cuda_graph_capture_replays_the_pipeline():
     assert torch.equal(a1, e1) and torch.equal(a2, e2) and torch.equal(a1b, e1)
     with pytest.raises(RuntimeError, match="captured"):
         g(w1[:1])
+
+
+def test_fp16_range_guard_raises_or_falls_back():
+    """Activations beyond the fp16 range (first-layer weights scaled by 1e7: d1 has no norm, so its output -- an fp16
+    operand of d2 in the fp16 modes -- leaves the 65504 range): a checked call raises OverflowError, or, with
+    fp16_overflow="fallback", re-runs in bf16x3 (bf16 planes, fp32 range) and matches the oracle; an unchecked call leaves
+    the sticky flag for range_overflow()."""
+    import model
+    from phasegen import synth
+    from phasegen.pipeline import PhaseGenPipeline
+    n_fft, hop, T, B = 256, 64, 40, 2
+    C = n_fft // 2
+    torch.manual_seed(51)
+    net = model.UNetModel(C, 2 * C).cuda()
+    synth.randomize_norm_affine(net, seed=52)
+    with torch.no_grad():
+        net.model._parts["down"].weight.mul_(1.0e7)
+    sd = {k: v.detach().cpu() for k, v in net.model.state_dict().items()}
+    wave = synth.synthetic_waves(B, (T - 1) * hop, sr=16000, seed=53, device="cuda")
+    strict = PhaseGenPipeline(net, n_fft, hop, precision="f16mix", per_clip=True, phase_only=True)
+    strict(wave)                                            # unchecked: runs, flag stays
+    assert strict.range_overflow() and not strict.range_overflow()
+    with pytest.raises(OverflowError, match="fp16 range"):
+        strict(wave, check_finite=True)
+    soft = PhaseGenPipeline(net, n_fft, hop, precision="f16mix", per_clip=True, phase_only=True, fp16_overflow="fallback")
+    audio, logmag, phase = soft(wave, check_finite=True, return_intermediates=True)
+    for b in range(B):
+        w = wave[b].cpu().numpy().astype(np.float64)
+        lm = np.log1p(np.abs(stft_np.stft(w, n_fft, hop)[1:]))
+        out = unet_torch.unet_forward(sd, torch.from_numpy(lm)[None], torch.float64, per_clip_bn=True)[0].numpy()
+        assert rel_l2(phase[b].cpu().numpy().T, out[:C]) < 1e-3
+    ok = PhaseGenPipeline(model.UNetModel(C, 2 * C).cuda(), n_fft, hop, precision="f16mix", per_clip=True, phase_only=True)
+    ok(wave, check_finite=True)                             # ordinary weights: no flag
+    assert not ok.range_overflow()

@@ -289,3 +289,137 @@ def test_async_checkpoint_equals_sync_checkpoint(tmp_path):
     assert set(a) == set(b)
     assert int(a["model.4.num_batches_tracked"]) + 1 == int(b["model.4.num_batches_tracked"])
     assert torch.equal(a["model.0.weight"], b["model.0.weight"])
+
+
+def test_config3_shape_training_parity():
+    """BASELINE.json config 3 at its own shape -- UNetModel(1024, 2048), 128-frame pairs, bf16 products and bf16 weight
+    gradients (batch 8 instead of 32 to keep the checker quick; tile plans depend on B only through the tile count).
+    This shape takes code paths the small cases do not: merged-clip MMAs with two MMA groups per weight tile, 512-column
+    accumulators, the wide (256 input channels x 2 taps) weight-gradient form, CTA pairs in forward and data gradient.
+      (a) forward vs the float64 oracle (run on the GPU in float64: same restatement, torch does the arithmetic);
+          bound 3e-2 relative L2 on the network output = the separately stated loose bf16 bound;
+      (b) every data / weight gradient of the tensor-core kernels vs the exact-fp32 SIMT kernels from an IDENTICAL
+          forward state, bound 2e-2 (bf16 operand rounding, bf16 gradient storage);
+      (c) one TrainStep vs a float64 reference step: loss within 3e-2, every weight gradient by direction
+          (cosine >= 0.98), the first Adam update (-lr * g / (|g| + eps)) by direction (cosine >= 0.9: elements whose
+          gradient is within the bf16 noise of zero flip the sign of their +-lr update)."""
+    import model
+    from phasegen import synth
+    from phasegen.train import TrainStep
+    C, T, B = 1024, 128, 8
+    dev = torch.device("cuda")
+    torch.manual_seed(21)
+    net = model.UNetModel(C, 2 * C).to(dev)
+    synth.randomize_norm_affine(net, seed=22)
+    sd = {k: v.detach().clone() for k, v in net.model.state_dict().items()}
+    g = torch.Generator().manual_seed(23)
+    sigma = 4.0 / (1.0 + torch.arange(C, dtype=torch.float32) / 32.0)
+    re, im = torch.randn(B, T, C, generator=g) * sigma, torch.randn(B, T, C, generator=g) * sigma
+    lm = torch.log1p(torch.sqrt(re * re + im * im)).contiguous().to(dev)
+    ph = torch.atan2(im, re).contiguous().to(dev)
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    cos = lambda a, b: float(torch.dot(a.double().reshape(-1), b.double().reshape(-1)) / (a.double().norm() * b.double().norm()))
+
+    # ---- float64 reference (oracle on the GPU): forward, loss, gradients
+    x_cf = lm.permute(0, 2, 1).contiguous().double()
+    target = torch.stack([x_cf, ph.permute(0, 2, 1).double()], 1)
+    ref_out = unet_torch.unet_forward(sd, x_cf, torch.float64)
+    ref_loss, _, _, ref_g = unet_torch.loss_and_grads(sd, x_cf, target, torch.float64)
+
+    # ---- (a) forward
+    dn, up = net._norm_params(dev)
+    tc = net.train_executor(B, T, dev, precision="bf16", grad_dtype=torch.bfloat16)
+    tc.load_input_cl(lm)
+    tc.run(dn, up)
+    e_out = rel(tc.out.permute(0, 2, 1), ref_out)
+    print(f"config-3 shape forward (bf16) vs float64 oracle: rel-L2 {e_out:.2e}")
+    assert e_out < 3e-2
+
+    # ---- (b) backward kernels on an identical forward state
+    simt = net.train_executor(B, T, dev, precision="fp32_simt")
+    simt.load_input_cl(lm)
+    simt.run(dn, up)
+    for i in range(simt.D):
+        tc.z[i].copy_(simt.z[i]); tc.g[i].copy_(simt.g[i])
+        for name in ("dn_ss", "dn_mv", "up_ss", "up_mv"):
+            if getattr(simt, name)[i] is not None:
+                getattr(tc, name)[i].copy_(getattr(simt, name)[i])
+    d_out = torch.randn(B, T, 2 * C, device=dev, generator=torch.Generator(device=dev).manual_seed(24)) * 1e-3
+    simt.backward(dn, up, d_out=d_out); tc.backward(dn, up, d_out=d_out)
+    torch.cuda.synchronize()
+    worst = 0.0
+    for i in range(simt.D):
+        errs = [rel(tc.dw_up[i], simt.dw_up[i]), rel(tc.dw_dn[i], simt.dw_dn[i]), rel(tc.din_up[i], simt.din_up[i])]
+        if simt.din_dn[i] is not None:
+            errs.append(rel(tc.din_dn[i], simt.din_dn[i]))
+        worst = max(worst, max(errs))
+        assert max(errs) < 2e-2, (i, errs)
+    print(f"config-3 shape wgrad/dgrad (bf16, bf16 gradients) vs exact SIMT: worst rel-L2 {worst:.2e}")
+    del simt
+    net.__dict__["_exec"] = {k: v for k, v in net._exec.items() if v is tc}
+
+    # ---- (c) one optimisation step
+    w_before = {k: p.detach().clone() for k, p in net.model.named_parameters()}
+    step = TrainStep(net, B, T, dev, precision="bf16")
+    assert step.ex is tc and step.grad_dtype == torch.bfloat16
+    loss3 = step(lm, ph)
+    torch.cuda.synchronize()
+    assert abs(float(loss3[0]) - ref_loss) < 3e-2 * abs(ref_loss), (float(loss3[0]), ref_loss)
+    grads = dict(zip((n for n, _ in net.model.named_parameters()), net._param_grads(tc)))
+    lr, eps = 1e-3, 1e-8
+    worst_g, worst_u = 1.0, 1.0
+    for k, p in net.model.named_parameters():
+        assert bool(torch.isfinite(p).all()), k
+        rg = ref_g[k]
+        c_g = cos(grads[k].float(), rg)
+        d_ref = -lr * rg / (rg.abs() + eps)
+        c_u = cos(p.detach() - w_before[k], d_ref)
+        worst_g, worst_u = min(worst_g, c_g), min(worst_u, c_u)
+        assert c_g > 0.98, (k, c_g)
+        assert c_u > 0.9, (k, c_u)
+    print(f"config-3 shape TrainStep vs float64 step: loss {float(loss3[0]):.5f} vs {ref_loss:.5f}, worst gradient cosine "
+          f"{worst_g:.4f}, worst update cosine {worst_u:.4f}")
+
+
+def test_backward_after_a_second_forward_raises():
+    """One set of activation buffers per shape: a backward whose forward state was overwritten by a later forward of the
+    same shape must raise instead of returning gradients of the wrong graph; forward/backward pairs accumulate fine."""
+    import model
+    C, B, T = 8, 2, 24
+    torch.manual_seed(3)
+    net = model.UNetModel(C, 2 * C).cuda()
+    x1, x2 = torch.randn(B, C, T, device="cuda"), torch.randn(B, C, T, device="cuda")
+    y1 = net.forward(x1)
+    y2 = net.forward(x2)
+    with pytest.raises(RuntimeError, match="overwritten by a later forward"):
+        (y1.sum() + y2.sum()).backward()
+    net.zero_grad()
+    net.forward(x1).sum().backward()
+    g1 = [p.grad.clone() for p in net.parameters()]
+    net.forward(x2).sum().backward()                       # accumulates into p.grad like any autograd node
+    net.zero_grad()
+    net.forward(x2).sum().backward()
+    g2 = [p.grad.clone() for p in net.parameters()]
+    net.zero_grad()
+    net.forward(x1).sum().backward(); net.forward(x2).sum().backward()
+    for p, a, b in zip(net.parameters(), g1, g2):
+        assert torch.allclose(p.grad, a + b, rtol=1e-5, atol=1e-6)
+
+
+def test_async_checkpoint_is_a_snapshot_of_the_call_time(tmp_path):
+    """save_async on a model large enough (C = 512: 0.6 GB) that the pinned-host copy is still in flight when the
+    weights are overwritten right after the call: the file must hold the weights of the call time, not a mixture."""
+    import model
+    torch.manual_seed(5)
+    net = model.UNetModel(512, 1024).cuda()
+    want = {k: v.detach().cpu().clone() for k, v in net.model.state_dict().items()}
+    path = str(tmp_path / "snap.pt")
+    h = net.save_async(path)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(1.0)                                    # the "next optimiser step", queued immediately
+    h.wait()
+    got = torch.load(path, map_location="cpu")
+    assert set(got) == set(want)
+    for k in want:
+        assert torch.equal(got[k], want[k]), k

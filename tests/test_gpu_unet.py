@@ -159,3 +159,54 @@ def test_executor_cache_is_bounded():
         assert len(net._exec) == 3
         again = net.forward(x[24])                               # evicted, rebuilt
     assert torch.equal(first, again) and len(net._exec) == 3
+
+
+def test_eval_mode_uses_running_statistics(monkeypatch):
+    """model.eval(): nn.BatchNorm semantics (running statistics), against the oracle with its train-mode norm swapped for
+    the eval-mode formula; train() restores the batch-statistics path.  The reference never calls eval(); kept for API parity."""
+    import model
+    from phasegen import synth
+    C, B, T = 64, 3, 40
+    torch.manual_seed(31)
+    net = model.UNetModel(C, 2 * C).cuda()
+    synth.randomize_norm_affine(net, seed=32)
+    g = torch.Generator().manual_seed(33)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(0.2 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+    sd = {k: v.detach().cpu() for k, v in net.model.state_dict().items()}
+    x = torch.randn(B, C, T)
+
+    def bn_eval(y, sd_, prefix, per_clip, dt):
+        v = lambda n: sd_[prefix + n].to(dt).view(1, -1, 1)
+        return (y - v(".running_mean")) / torch.sqrt(v(".running_var") + unet_torch.BN_EPS) * v(".weight") + v(".bias")
+    ref_train = unet_torch.unet_forward(sd, x, torch.float64)
+    monkeypatch.setattr(unet_torch, "_bn_train", bn_eval)
+    ref_eval = unet_torch.unet_forward(sd, x, torch.float64)
+    rel = lambda a, b: float((a.double().cpu() - b).norm() / b.norm())
+    net.eval()
+    with torch.no_grad():
+        assert rel(net.forward(x.cuda()), ref_eval) < 2e-4
+    net.train()
+    with torch.no_grad():
+        assert rel(net.forward(x.cuda()), ref_train) < 2e-4
+    assert rel(torch.from_numpy(np.asarray(ref_eval)), ref_train) > 1e-2     # the two modes really differ
+
+
+def test_invalidate_packed_after_a_data_write():
+    """Writes through .data bump neither data_ptr nor _version: invalidate_packed() is the documented way to re-pack."""
+    import model
+    C, B, T = 64, 2, 40
+    torch.manual_seed(41)
+    net = model.UNetModel(C, 2 * C).cuda()
+    x = torch.randn(B, C, T, device="cuda")
+    with torch.no_grad():
+        y0 = net.forward(x).clone()
+        for p in net.parameters():
+            if p.dim() == 3:
+                p.data.mul_(1.5)
+        net.invalidate_packed()
+        y1 = net.forward(x).clone()
+    assert float((y1 - y0).abs().max()) > 1e-3

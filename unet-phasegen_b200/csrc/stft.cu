@@ -333,6 +333,42 @@ __global__ void peak_normalize_kernel(float* __restrict__ wave, const unsigned* 
     }
 }
 
+// Long-form stitching (BASELINE.json config 4): windows of `win` samples every `step` samples (step >= win/2, so at
+// most two overlap) are cross-faded with a periodic-Hann ramp over the ov = win - step shared samples (rising half on
+// the later window, falling half on the earlier one: the two gains sum to one).  Window i sits at slot
+// (i % world) * per_rank + i / world of `windows` -- the layout an all-gather of round-robin-dealt windows produces
+// (world = 1: plain order).  One pass, gather form: no atomics on the output; the global peak is one atomicMax per warp.
+__global__ void __launch_bounds__(256)
+stitch_kernel(const float* __restrict__ windows, int n_windows, int win, int step, int world, int per_rank,
+              float* __restrict__ out, long long n_out, unsigned* __restrict__ peak_bits) {
+    const int ov = win - step;
+    const float inv_ov = ov > 0 ? 1.0f / (float)ov : 0.f;
+    float pk = 0.f;
+    for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n_out; n += (long long)gridDim.x * blockDim.x) {
+        long long i1 = n / step; if (i1 > n_windows - 1) i1 = n_windows - 1;
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const long long i = i1 - q;
+            if (i < 0) continue;
+            const long long o = n - i * step;
+            if (o >= win) continue;
+            float g = 1.f;
+            if (i > 0 && o < ov) g = 0.5f - 0.5f * cospif((float)o * inv_ov);                               // rising half
+            else if (i < n_windows - 1 && o >= win - ov) g = 0.5f + 0.5f * cospif((float)(o - (win - ov)) * inv_ov);   // falling half
+            const size_t slot = (size_t)(i % world) * per_rank + (size_t)(i / world);
+            acc = fmaf(__ldg(windows + slot * win + o), g, acc);
+        }
+        out[n] = acc;
+        pk = fmaxf(pk, fabsf(acc));
+    }
+    if (peak_bits) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+        if ((threadIdx.x & 31) == 0 && pk > 0.f) atomicMax(peak_bits, __float_as_uint(pk));
+    }
+}
+
 template <int NC>
 static int launch_stft(const float* wave, int B, int N, int T, const float* tw, int mode, float* a, float* bq,
                        uint16_t* hi, uint16_t* lo, long long bs, int fmt, cudaStream_t st, const float* proj_mag = nullptr,
@@ -467,4 +503,17 @@ extern "C" int pg_peak_normalize(float* wave, const float* peak, int B, int N, p
     pg::peak_normalize_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         wave, reinterpret_cast<const unsigned*>(peak), N);
     return pg::check_launch("peak_normalize_kernel");
+}
+
+extern "C" int pg_stitch(const float* windows, int n_windows, int win, int step, int world, int per_rank, float* out,
+                         int64_t n_out, float* peak, pg_stream stream) {
+    PG_REQUIRE(windows && out && n_windows > 0 && win > 0 && n_out > 0, "pg_stitch: bad arguments");
+    PG_REQUIRE(step > 0 && step <= win && 2 * step >= win, "pg_stitch: step must lie in [win/2, win] (got win=%d step=%d)", win, step);
+    PG_REQUIRE(world >= 1 && per_rank >= (n_windows + world - 1) / world, "pg_stitch: per_rank too small for %d windows on %d ranks", n_windows, world);
+    PG_REQUIRE(n_out <= (int64_t)win + (int64_t)(n_windows - 1) * step, "pg_stitch: n_out exceeds the span of the windows");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (peak) cudaMemsetAsync(peak, 0, sizeof(float), st);
+    long long blocks = (n_out + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16;
+    pg::stitch_kernel<<<(int)blocks, 256, 0, st>>>(windows, n_windows, win, step, world, per_rank, out, n_out, reinterpret_cast<unsigned*>(peak));
+    return pg::check_launch("stitch_kernel");
 }

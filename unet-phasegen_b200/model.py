@@ -253,9 +253,17 @@ class UNetModel(nn.Module):
         ws = [b._parts["down"].weight for b in blocks] + [b._parts["up"].weight for b in blocks]
         return ws, tuple((w.data_ptr(), w._version) for w in ws) + (self.__dict__.get("_native_updates", 0),)
 
+    def _sync_state(self):
+        """Hook of a sharded data-parallel optimiser (phasegen.train.TrainStep): bring the fp32 master weights of
+        this rank up to date before they are read as a whole (checkpoint, re-packing for another executor)."""
+        hook = self.__dict__.get("_pre_state_hook")
+        if hook is not None:
+            hook()
+
     def _ensure_packed(self, ex):
         ws, stamp = self._weight_stamp()
         if self._packed.get(id(ex)) != stamp:
+            self._sync_state()
             n = len(ws) // 2
             ex.pack_weights(ws[:n], ws[n:])
             self._packed[id(ex)] = stamp
@@ -350,6 +358,7 @@ class UNetModel(nn.Module):
         return self._run(ex, dn, up)
 
     def save(self, path):
+        self._sync_state()
         torch.save({k: v.detach().cpu() for k, v in self.model.state_dict().items()}, path)
 
     def save_async(self, path):
@@ -358,6 +367,7 @@ class UNetModel(nn.Module):
         copy has been ordered after the work already queued.  Returns a handle whose ``.wait()`` joins the writer.
         The file is the same inner-block ``state_dict`` the reference writes (model.py:45-48)."""
         import threading
+        self._sync_state()
         sd = self.model.state_dict()
         dev = next(self.parameters()).device
         if dev.type != "cuda":

@@ -58,6 +58,7 @@ _SIGNATURES = {
     "pg_stft_pairs": (_I, [_P, _I, _I, _I, _I, _P, _F, _F, _P, _P, _P]),
     "pg_istft": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P]),
     "pg_peak_normalize": (_I, [_P, _P, _I, _I, _P]),
+    "pg_stitch": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _P, _P]),
     "pg_pack_weight": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "pg_conv_tc": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, C.POINTER(ConvEpilogue), _P]),
     "pg_conv_epilogue_supported": (_I, [C.POINTER(ConvDesc), _I]),

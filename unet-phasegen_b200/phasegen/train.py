@@ -169,8 +169,13 @@ class TrainStep:
     phase [B, T, C]."""
 
     def __init__(self, net, B, T, device, precision="bf16", lr=1e-3, betas=(0.9, 0.999), eps=1e-8, mag_weight=0.2,
-                 grad_dtype=None):
-        """grad_dtype: dtype of the weight gradients the wgrad kernel writes, NCCL reduces and Adam reads:
+                 grad_dtype=None, shard_optimizer=None, reserve_ctas=None, data_parallel=True):
+        """shard_optimizer: data-parallel runs only.  True (default when world_size > 1) = reduce-scatter the weight
+        gradients, update 1/world of (master weights, Adam moments) per rank, all-gather the refreshed operand planes
+        (phasegen/sharded.py); False = all-reduce + replicated Adam.  data_parallel=False ignores an initialised process
+        group (a purely local step, e.g. a reference replica inside a distributed check).  reserve_ctas: cap of the persistent grids of the
+        backward tensor-core kernels in data-parallel runs (default 132 of 148: 16 SMs stay free for NCCL).
+        grad_dtype: dtype of the weight gradients the wgrad kernel writes, NCCL reduces and Adam reads:
         "fp32" (default for the fp32-class precisions: what autograd would give) or "bf16" (default for
         precision="bf16", on any number of GPUs: half the all-reduce volume -- 1.22 GB instead of 2.45 GB for
         UNetModel(1024, 2048) -- and 2 B/parameter less HBM traffic in wgrad and in Adam; moments and master
@@ -182,14 +187,25 @@ class TrainStep:
             for conv, kind in ((b._parts["down"], PG_CONV), (b._parts["up"], PG_CONV_TRANSPOSE)):
                 if ops.packed_view(conv.weight, kind) is None:
                     conv.weight.data = ops.to_packed_storage(conv.weight.data, kind)
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.world = dist.get_world_size() if data_parallel and dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        if self.world > 1:
+            # replicas must start identical (DDP broadcasts at wrap time): parameters and norm buffers from rank 0
+            with torch.no_grad():
+                for t in list(net.parameters()) + list(net.buffers()):
+                    dist.broadcast(t.data, 0)
+            net.invalidate_packed()
         if grad_dtype is None:
             grad_dtype = "bf16" if precision == "bf16" else "fp32"
         self.grad_dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[grad_dtype]
         self.ex = net.train_executor(B, T, device, precision, grad_dtype=self.grad_dtype)
         if self.world > 1 and self.ex.prec != PG_PREC_FP32_SIMT:
-            self.ex.reserve_sms_in_backward(132)
+            import os
+            n_res = int(os.environ.get("PG_DDP_CTAS", "132")) if reserve_ctas is None else int(reserve_ctas)
+            if 0 < n_res < 148:
+                self.ex.reserve_sms_in_backward(n_res)
         self.t = 0
+        self._works = []
         ex = self.ex
         tc = ex.prec != PG_PREC_FP32_SIMT
         # (parameter storage, gradient buffer, bf16 planes to refresh) in packed order
@@ -205,13 +221,63 @@ class TrainStep:
                 for prm, g in ((nm.weight, dgb[0]), (nm.bias, dgb[1])):
                     if prm.requires_grad:
                         self.items.append(dict(p=prm.data, g=g, conv=None))
+        # sharded optimiser: conv weights whose element count splits evenly over the ranks
+        self.sharded = None
+        if shard_optimizer is None:
+            shard_optimizer = self.world > 1
+        if shard_optimizer and self.world > 1:
+            from .sharded import ShardedUpdater
+            self.sharded = ShardedUpdater(self._adam_slice)
+            for it in self.items:
+                if it["conv"] is not None and ShardedUpdater.can_shard(it["p"].numel(), self.world):
+                    which, i = it["conv"]
+                    hi, lo = (ex.wd[i] if which == "dn" else ex.wu[i])[:2]
+                    it["key"] = it["g"].data_ptr()
+                    it["sh"] = self.sharded.add(it["key"], it["p"].view(-1), it["g"].view(-1),
+                                                [hi.view(-1), lo.view(-1) if lo is not None else None])
+                    it["planes"] = id(hi)
+            net.__dict__["_pre_state_hook"] = self.sync_master
         for it in self.items:
+            if "sh" in it:
+                continue                           # moments live (sliced) in the sharded updater
             it["m"] = torch.zeros_like(it["p"]); it["v"] = torch.zeros_like(it["p"])
 
+    def _adam_slice(self, p, g, m, v, planes):
+        hi = planes[0] if planes else None
+        lo = planes[1] if len(planes) > 1 else None
+        ops.adam_step(p, g, m, v, self.lr, self.betas[0], self.betas[1], self.eps, self.t, 1.0 / self.world, hi, lo)
+
+    def sync_master(self):
+        """Sharded optimiser: all-gather the fp32 master weights so that every rank holds the current model (needed
+        before a checkpoint, or before another executor re-packs its operand planes).  A collective."""
+        if self.sharded is not None:
+            self.sharded.sync_master()
+
     def __call__(self, logmag_cl, phase_cl):
+        loss3 = self.forward_backward(logmag_cl, phase_cl)
+        self.apply()
+        return loss3
+
+    def forward_backward(self, logmag_cl, phase_cl):
+        """Forward, loss and backward of one batch; gradient collectives are started as the layers finish.  Leaves the
+        (local, or in-flight reduced) gradients in the executor; `apply()` completes the step."""
         import torch.distributed as dist
         net, ex = self.net, self.ex
+        logmag_cl = ops._need_cuda(logmag_cl, "logmag_cl")
+        phase_cl = ops._need_cuda(phase_cl, "phase_cl")
+        if tuple(logmag_cl.shape) != (ex.B, ex.T, ex.levels[0].down.C_in) or phase_cl.shape != logmag_cl.shape:
+            raise RuntimeError(f"phasegen: TrainStep was built for channels-last pairs of shape "
+                               f"{(ex.B, ex.T, ex.levels[0].down.C_in)}, got {tuple(logmag_cl.shape)} / {tuple(phase_cl.shape)}")
         net._ensure_packed(ex)
+        if self.sharded is not None:
+            # each layer's refreshed planes are awaited right before the first kernel that reads them
+            pending = {it["planes"]: it["key"] for it in self.items if "sh" in it}
+
+            def ready(w):
+                key = pending.get(id(w[0]))
+                if key is not None:
+                    self.sharded.wait_planes(key)
+            ex.weight_ready = ready
         ex.load_input_cl(logmag_cl)
         dn, up = net._norm_params(logmag_cl.device)
         ex.run(dn, up)
@@ -220,12 +286,26 @@ class TrainStep:
         loss3 = ex.loss(logmag_cl, phase_cl, self.mag_weight)
         works = []                                  # (gradient tensor, NCCL work) in the order backward finishes them
         if self.world > 1:
-            # one NCCL all-reduce per weight gradient, issued as soon as that layer's wgrad is queued
-            # (the outermost transposed conv, 44 % of the parameters, goes first), overlapping the
-            # remaining dgrad / wgrad kernels
-            ex.grad_hook = lambda g: works.append((g, dist.all_reduce(g, async_op=True)))
+            # one NCCL collective per weight gradient, issued as soon as that layer's wgrad is queued (the outermost
+            # transposed conv, 44 % of the parameters, goes first), overlapping the remaining dgrad / wgrad kernels:
+            # a reduce-scatter for sharded items, an all-reduce for the rest
+            sharded_keys = set(self.sharded.items) if self.sharded is not None else ()
+
+            def hook(g):
+                if g.data_ptr() in sharded_keys:
+                    self.sharded.grad_ready(g.data_ptr())
+                else:
+                    works.append((g, dist.all_reduce(g, async_op=True)))
+            ex.grad_hook = hook
         ex.backward(dn, up)
         ex.grad_hook = None
+        self._works = works
+        return loss3
+
+    def apply(self):
+        """Adam (train.py:62) on the gradients of the last forward_backward(), refreshing the operand planes."""
+        import torch.distributed as dist
+        net, ex, works = self.net, self.ex, self._works
         self.t += 1
         scale = 1.0 / self.world
 
@@ -237,11 +317,13 @@ class TrainStep:
             ops.adam_step(it["p"], it["g"], it["m"], it["v"], self.lr, self.betas[0], self.betas[1], self.eps, self.t, scale, hi, lo)
 
         if self.world > 1:
-            # each layer's Adam update is queued behind that layer's all-reduce only, so it runs while the
-            # all-reduces of the layers backward reached later are still on the wire
+            # each layer's Adam update is queued behind that layer's collective only, so it runs while the
+            # collectives of the layers backward reached later are still on the wire
             flat = dist.all_reduce(ex.dgb_flat, async_op=True)
             by_grad = {it["g"].data_ptr(): it for it in self.items}
-            done = set()
+            done = set(id(it) for it in self.items if "sh" in it)
+            if self.sharded is not None:
+                self.sharded.finish()
             for g, w in works:
                 w.wait()
                 it = by_grad.get(g.data_ptr())
@@ -259,7 +341,6 @@ class TrainStep:
             ws = [b._parts["down"].weight for b in blocks] + [b._parts["up"].weight for b in blocks]
             ex.pack_weights(ws[:len(blocks)], ws[len(blocks):])
         net._mark_packed(ex)
-        return loss3
 
     # ------------------------------------------------------------------ checkpoint / resume
     def _named_items(self):
@@ -283,9 +364,13 @@ class TrainStep:
         from ._lib import PG_CONV, PG_CONV_TRANSPOSE
         params = dict(self.net.model.named_parameters())
         state = {}
+        self.sync_master()
         for name, it in self._named_items():
             p = params[name]
-            m, v = it["m"], it["v"]
+            if "sh" in it:                        # sharded moments: gather the slices (a collective on every rank)
+                m, v = (t.view(it["p"].shape) for t in self.sharded.full_moments(it["key"]))
+            else:
+                m, v = it["m"], it["v"]
             if m.dim() == 3:                      # conv weights: packed [k][C_out][C_in] -> torch layout
                 perm = (2, 1, 0) if self._is_transposed(name) else (1, 2, 0)
                 m, v = m.permute(*perm), v.permute(*perm)
@@ -298,13 +383,18 @@ class TrainStep:
             if name not in sd["state"]:
                 raise KeyError(f"phasegen: optimiser state for '{name}' missing from the checkpoint")
             p = params[name]
-            for key, dst in (("exp_avg", it["m"]), ("exp_avg_sq", it["v"])):
-                src = sd["state"][name][key].to(dst.device, torch.float32)
+            full = {}
+            for key in ("exp_avg", "exp_avg_sq"):
+                src = sd["state"][name][key].to(it["p"].device, torch.float32)
                 if tuple(src.shape) != tuple(p.shape):
                     raise RuntimeError(f"phasegen: optimiser state '{name}.{key}' has shape {tuple(src.shape)}, expected {tuple(p.shape)}")
-                if dst.dim() == 3:
+                if it["p"].dim() == 3:
                     src = src.permute(2, 1, 0) if self._is_transposed(name) else src.permute(2, 0, 1)
-                dst.copy_(src)
+                full[key] = src.contiguous()
+            if "sh" in it:
+                self.sharded.load_moments(it["key"], full["exp_avg"], full["exp_avg_sq"])
+            else:
+                it["m"].copy_(full["exp_avg"]); it["v"].copy_(full["exp_avg_sq"])
         self.t = int(sd["step"])
         self.lr, self.betas, self.eps = float(sd["lr"]), tuple(sd["betas"]), float(sd["eps"])
 

@@ -195,6 +195,7 @@ class UNetExecutor:
             self.z = [scratch] * D
             self.g = [scratch] * D
         self._out = None                                        # normalised last-layer output, allocated on first use
+        self.weight_ready = None                                # optional callable(w): called before a kernel reads weight planes w
 
     @property
     def out(self):
@@ -274,6 +275,8 @@ class UNetExecutor:
 
     # ------------------------------------------------------------------------------ forward
     def _conv(self, desc, src, w, y, stats):
+        if self.weight_ready is not None:
+            self.weight_ready(w)
         if self.prec == PG_PREC_FP32_SIMT:
             ops.conv_simt(desc, src.hi, w[2], y)
             if stats is not None:
@@ -295,6 +298,8 @@ class UNetExecutor:
     def _layer(self, mode, desc, src, w, y, stats, ss, mv, norm, running, dst0, dst1=None):
         """One convolution + (norm) + activation fan-out, in the form chosen at construction."""
         if mode != PG_EPI_RAW:
+            if self.weight_ready is not None:
+                self.weight_ready(w)
             gamma, beta, eps = norm if norm is not None else (None, None, BN_EPS_DEFAULT)
             ops.conv_tc(desc, src.hi, src.lo, w[0], w[1], None, None,
                         ops.conv_epilogue(mode, dst0, dst1, gamma, beta, eps))
