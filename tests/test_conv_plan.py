@@ -87,8 +87,8 @@ def test_whole_clip_tiles_for_the_fused_norm_epilogue():
     assert (u2["whole_clip"], u2["n_ntiles"], u2["nb"], u2["acc_stages"]) == (1, 2, 1, 1)
     u3, _ = plan("u3", 512, 696, 256, "f16x3", whole_clip=1)          # both output phases side by side
     assert (u3["whole_clip"], u3["OS"], u3["n_ntiles"], u3["n_tile"], u3["acc_stages"]) == (1, 2, 1, 176, 1)
-    u4, _ = plan("u4", 512, 696, 256, "f16x3", whole_clip=1)          # two phases of 96 columns: un-merged, double-buffered
-    assert (u4["whole_clip"], u4["merged"], u4["nb"], u4["acc_stages"]) == (1, 0, 1, 2)
+    _, du4 = plan("u4", 512, 696, 256, "f16x3")                       # short two-phase layer: stays merged, two-pass norm
+    assert _lib.load().pg_conv_epilogue_supported(ctypes.byref(du4), _lib.PG_EPI_NORM_ACT) == 0
     d3, d = plan("d3", 512, 696, 256, "f16x3", whole_clip=1)          # one part: the ordinary tile already is a whole clip
     assert (d3["whole_clip"], d3["n_ntiles"], d3["OS"]) == (0, 1, 1)
     lib = _lib.load()
@@ -99,5 +99,5 @@ def test_whole_clip_tiles_for_the_fused_norm_epilogue():
     # training shape: merged single-phase tiles already hold whole clips; two-phase layers are un-merged on request
     d3t, _ = plan("d3", 1024, 128, 32, "bf16", whole_clip=1)
     assert d3t["merged"] == 1 and d3t["whole_clip"] == 0
-    u3t, _ = plan("u3", 1024, 128, 32, "bf16", whole_clip=1)
-    assert u3t["merged"] == 0 and u3t["whole_clip"] == 1
+    _, du3t = plan("u3", 1024, 128, 32, "bf16")
+    assert lib.pg_conv_epilogue_supported(ctypes.byref(du3t), _lib.PG_EPI_NORM_ACT) == 0

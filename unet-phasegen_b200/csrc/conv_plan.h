@@ -192,9 +192,11 @@ static inline int conv_plan_build(const pg_conv_desc* d, ConvPlan* p) {
     p->whole_clip = 0;
     if (d->tc_whole_clip) {
         const int parts = p->OS * p->n_ntiles;
-        if (p->merged && p->OS > 1) {                                 // re-plan without merging (short two-phase layers)
-            p->merged = 0; p->mgroups = 1; p->nb = 1;
-            p->strip_rows = (n_cta + max_shift + 7) / 8 * 8;
+        if (p->merged && p->OS > 1) {
+            // short two-phase layers: un-merging them costs more (N = 96 MMAs: measured 0.96 -> 1.58 ms on u4 at the
+            // BASELINE shape) than the separate normalising pass saves, so they keep the two-pass form
+            set_error("conv plan: merged two-phase tiles do not hold a whole clip");
+            return PG_ERR_UNSUPPORTED;
         }
         if (!p->merged) {
             if (parts * p->n_tile > 512) { set_error("conv plan: a whole clip needs %d accumulator columns (> 512)", parts * p->n_tile); return PG_ERR_UNSUPPORTED; }

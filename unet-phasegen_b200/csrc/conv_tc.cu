@@ -59,6 +59,7 @@ struct ConvTcParams {
     const float* gamma; const float* beta; float eps;
     ActDst dst0, dst1;
     float2* ss_out;                 // NORM_ACT: optional [B][C_out] (scale, shift) record of what was applied
+    int scalar_raw_stores;          // A/B hook (PG_TC_SCALAR_STORES=1): RAW epilogue stores one fp32 per thread instead of staging
 };
 // plan.pair = 1: tiles are 256 output channels wide and owned by a CTA pair; plan.strip_rows is then the
 // HALF strip each CTA loads (n_tile/2 + largest shift rows).
@@ -114,6 +115,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
     uint64_t* accFull = emptyB + 2;           // [2]
     uint64_t* accEmpty = accFull + 2;         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accEmpty + 2);
+    uint32_t* epi_tiles = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);   // 4 warps x [16 rows][32 ch] words
 
     // warp index through a shuffle: provably warp-uniform, so the role branches below are uniform branches and
     // the single-thread instructions' operands can live in uniform registers
@@ -232,13 +234,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
             int a_slot = 0; uint32_t a_ph = 0;
             // operand format field: 1 = bf16, 0 = fp16 (bits [7,10) for A, [10,13) for B)
             const int n_mma = pl.merged ? nb_grp * pl.strip_rows : pl.n_tile;
-            const int n_loop = pl.merged ? pl.mgroups : pl.nb * t_nts;    // merged: one MMA covers every clip of a group
+            // merged: one MMA covers every clip of a group (column step n_mma); else position tiles (outer) x clips (inner),
+            // strips laid out [position tile][clip], clip c's parts at columns c * (n_tile * parts per clip)
+            const int n_outer = pl.merged ? 1 : t_nts, n_inner = pl.merged ? pl.mgroups : pl.nb;
+            const uint32_t dcol_step = pl.merged ? (uint32_t)n_mma : (uint32_t)(pl.n_tile * t_phases * t_nts);
             const uint32_t idesc = (make_idesc_bf16(n_mma, PAIR ? 256 : 128) & ~(prm.f16 ? ((7u << 7) | (7u << 10)) : 0u)) |
                                    (prm.a_mn ? (1u << 15) : 0u);
             const bool a_mn = prm.a_mn != 0;
-            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc_flag) {
-                if (elect_one()) { if (PAIR) umma_bf16_pair(d, da, db, idesc, acc_flag); else umma_bf16(d, da, db, idesc, acc_flag); }
+            // descriptors travel as their low 32-bit words (tc_ptx.cuh): the issue loop only adds to start addresses
+            auto mma = [&](uint32_t d, uint32_t da, uint32_t db, uint32_t acc_flag) {
+                if (elect_one()) { if (PAIR) umma_words_pair(d, da, db, idesc, acc_flag); else umma_words(d, da, db, idesc, acc_flag); }
             };
+            const uint32_t a_step = a_mn ? (2048u >> 4) : (32u >> 4);   // +16 K elements: 2 atoms down (MN-major) / 32 B along (K-major)
             auto commit = [&](uint64_t* bar) {
                 if (elect_one()) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); }
                 __syncwarp();
@@ -253,11 +260,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                 const uint32_t strip_bytes = (uint32_t)pl.strip_rows * 128u;
                 // merged: MMA c covers the nb_grp clips of group c (columns c*n_mma ...); else one MMA per (position tile,
                 // clip) of the tile, part (phase, nt) of clip c at column ((c*t_phases + phase)*t_nts + nt)*n_tile
-                const uint32_t clip_bytes = pl.merged ? (uint32_t)nb_cta * strip_bytes : strip_bytes;
+                const uint32_t clip_step = (pl.merged ? (uint32_t)nb_cta * strip_bytes : strip_bytes) >> 4;   // descriptor units
                 for (int ch = 0; ch < pl.n_chunks; ++ch) {
                   for (int ph = tc.phase; ph < tc.phase + t_phases; ++ph) {
                     const int ng = pl.n_groups[ph];
-                    const int ph_sub = ph - tc.phase;
+                    const uint32_t dcol_ph = d_tmem + (uint32_t)((ph - tc.phase) * t_nts * pl.n_tile);
                     for (int g = 0; g < ng; ++g) {
                         const ConvGroup grp = pl.groups[ph][g];
                         const int bs = b_it & 1; const uint32_t bph = (b_it >> 1) & 1;
@@ -274,32 +281,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                             const uint32_t a_lo = a_hi + kATileBytes;
                             const uint32_t sh = (uint32_t)tp.shift * 128u;
                             const uint32_t acc_first = (ch | g | j) ? 1u : 0u;   // first MMA into this phase's columns overwrites
-                            for (int c = 0; c < n_loop; ++c) {     // one MMA group per clip (x position tile) of the bundle
-                                uint32_t boff, dcol;
-                                if (pl.merged) {
-                                    boff = (uint32_t)c * clip_bytes + sh;
-                                    dcol = d_tmem + (uint32_t)c * (uint32_t)n_mma;
-                                } else {
-                                    const int nt_sub = c / pl.nb, cc = c - nt_sub * pl.nb;     // strips are laid out [nt][clip]
-                                    boff = (uint32_t)c * clip_bytes + sh;
-                                    dcol = d_tmem + (uint32_t)(((cc * t_phases + ph_sub) * t_nts + nt_sub) * pl.n_tile);
-                                }
-#pragma unroll
-                                for (int kk = 0; kk < 4; ++kk) {   // 4 x (K = 16) per 64-channel chunk
-                                    const uint64_t da_hi = a_mn ? make_desc_sw128_mn(a_hi + kk * 2048, 8192) : make_desc_sw128(a_hi + kk * 32, 0);
-                                    const uint64_t db_hi = make_desc_sw128(b_hi + boff + kk * 32, prm.base_offset_mode);
+                            // one MMA group per (position tile, clip) of the bundle -- merged: per clip group.  Offsets advance by
+                            // additions only: this loop is the issue path of the tensor pipe (one MMA per ~88 tensor cycles
+                            // with two products per MAC), a runtime division per group starved it (measured: -31 %).
+                            const uint32_t aw_hi = a_mn ? desc_lo_sw128_mn(a_hi, 8192) : desc_lo_sw128(a_hi);
+                            const uint32_t aw_lo = a_mn ? desc_lo_sw128_mn(a_lo, 8192) : desc_lo_sw128(a_lo);
+                            uint32_t bw_hi = desc_lo_sw128(b_hi + sh), bw_lo = desc_lo_sw128(b_lo + sh);
+                            for (int o = 0; o < n_outer; ++o) {
+                                uint32_t dcol = dcol_ph + (uint32_t)o * (uint32_t)pl.n_tile;
+                                for (int c = 0; c < n_inner; ++c, bw_hi += clip_step, bw_lo += clip_step, dcol += dcol_step) {
                                     if (w_lo) {
-                                        const uint64_t da_lo = a_mn ? make_desc_sw128_mn(a_lo + kk * 2048, 8192) : make_desc_sw128(a_lo + kk * 32, 0);
-                                        const uint64_t db_lo = make_desc_sw128(b_lo + boff + kk * 32, prm.base_offset_mode);
-                                        mma(dcol, da_lo, db_hi, kk == 0 ? acc_first : 1u);
-                                        mma(dcol, da_hi, db_lo, 1);
-                                        mma(dcol, da_hi, db_hi, 1);
+#pragma unroll
+                                        for (uint32_t kk = 0; kk < 4; ++kk) {   // 4 x (K = 16) per 64-channel chunk
+                                            mma(dcol, aw_lo + kk * a_step, bw_hi + kk * 2, kk == 0 ? acc_first : 1u);
+                                            mma(dcol, aw_hi + kk * a_step, bw_lo + kk * 2, 1);
+                                            mma(dcol, aw_hi + kk * a_step, bw_hi + kk * 2, 1);
+                                        }
                                     } else if (x_lo) {
-                                        const uint64_t db_lo = make_desc_sw128(b_lo + boff + kk * 32, prm.base_offset_mode);
-                                        mma(dcol, da_hi, db_lo, kk == 0 ? acc_first : 1u);
-                                        mma(dcol, da_hi, db_hi, 1);
+#pragma unroll
+                                        for (uint32_t kk = 0; kk < 4; ++kk) {
+                                            mma(dcol, aw_hi + kk * a_step, bw_lo + kk * 2, kk == 0 ? acc_first : 1u);
+                                            mma(dcol, aw_hi + kk * a_step, bw_hi + kk * 2, 1);
+                                        }
                                     } else {
-                                        mma(dcol, da_hi, db_hi, kk == 0 ? acc_first : 1u);
+#pragma unroll
+                                        for (uint32_t kk = 0; kk < 4; ++kk) mma(dcol, aw_hi + kk * a_step, bw_hi + kk * 2, kk == 0 ? acc_first : 1u);
                                     }
                                 }
                             }
@@ -316,19 +322,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
         }
     } else {
         // ========================================================================= epilogue
+        // A thread owns one output channel (TMEM lane) and reads 16 consecutive positions per tcgen05.ld.  Storing them
+        // directly is one 2- or 4-byte store per element (64-128 B per warp instruction): measured, the global-store
+        // instruction rate -- not bytes -- then bounds the epilogue (+16 % on d1 with two fp16 destinations).  So every
+        // 16 x 32 chunk goes through a private shared-memory tile [16 rows][32 channels] of 32-bit words (conflict-free
+        // both ways) and leaves as 128-bit stores of 8 (16-bit planes) or 4 (fp32) consecutive channels of one row.
         const int q = warp & 3;                               // TMEM lane quarter this warp may read
+        uint32_t* tile = epi_tiles + q * 512;
         uint32_t t_it = 0;
-        const int col_pitch = pl.merged ? pl.strip_rows : pl.n_tile * t_phases * t_nts;   // accumulator columns per clip
         const int n_parts = t_phases * t_nts;
+        const int col_pitch = pl.merged ? pl.strip_rows : pl.n_tile * n_parts;   // accumulator columns per clip
         bool bad_range = false;
-        for (int tile = tile0; tile < n_tiles; tile += tile_step, ++t_it) {
-            TileCoord tc = decode_tile(pl, tile);
+        // fp32 rows: v[i] = value of row (row0 + i*OS) of this thread's channel, i < nv
+        auto store_f32 = [&](float* base, size_t off0, size_t row_pitch, const float* v, int nv) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tile[i * 32 + lane] = __float_as_uint(v[i]);
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int idx = lane + 32 * t, r = idx >> 3, part = idx & 7;
+                if (r < nv) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(tile + r * 32 + part * 4);
+                    *reinterpret_cast<uint4*>(base + off0 + (size_t)r * row_pitch + part * 4) = w;
+                }
+            }
+            __syncwarp();
+        };
+        // activation + hi/lo split into a consumer's operand planes (hi | lo << 16 per word in the tile)
+        auto store_split = [&](const ActDst& d, size_t off0, size_t row_pitch, const float* v, int nv) {
+            const int fmt = fmt_of_dtype(d.dtype);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float a = leaky(v[i], d.slope);
+                uint16_t h, l;
+                split16(a, fmt, h, l);
+                if (fmt == PG_FMT_F16 && i < nv) bad_range |= !f16_fits(a);
+                tile[i * 32 + lane] = (uint32_t)h | ((uint32_t)l << 16);
+            }
+            __syncwarp();
+            const bool two = d.dtype == PG_DT_BF16_SPLIT || d.dtype == PG_DT_F16_SPLIT;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int idx = lane + 32 * t, r = idx >> 2, part = idx & 3;
+                if (r < nv) {
+                    const uint4 w0 = *reinterpret_cast<const uint4*>(tile + r * 32 + part * 8);
+                    const uint4 w1 = *reinterpret_cast<const uint4*>(tile + r * 32 + part * 8 + 4);
+                    uint4 hv, lv;
+                    hv.x = __byte_perm(w0.x, w0.y, 0x5410); hv.y = __byte_perm(w0.z, w0.w, 0x5410);
+                    hv.z = __byte_perm(w1.x, w1.y, 0x5410); hv.w = __byte_perm(w1.z, w1.w, 0x5410);
+                    lv.x = __byte_perm(w0.x, w0.y, 0x7632); lv.y = __byte_perm(w0.z, w0.w, 0x7632);
+                    lv.z = __byte_perm(w1.x, w1.y, 0x7632); lv.w = __byte_perm(w1.z, w1.w, 0x7632);
+                    const size_t o = off0 + (size_t)r * row_pitch + part * 8;
+                    *reinterpret_cast<uint4*>(static_cast<uint16_t*>(d.hi) + o) = hv;
+                    if (two) *reinterpret_cast<uint4*>(static_cast<uint16_t*>(d.lo) + o) = lv;
+                }
+            }
+            __syncwarp();
+        };
+        for (int tile_i = tile0; tile_i < n_tiles; tile_i += tile_step, ++t_it) {
+            TileCoord tc = decode_tile(pl, tile_i);
             if (PAIR) tc.co_tile = tc.co_tile * 2 + rank;
             const int acc = pl.acc_stages == 2 ? (t_it & 1) : 0;
             const uint32_t acc_ph = pl.acc_stages == 2 ? ((t_it >> 1) & 1) : (t_it & 1);
             mbar_wait_sleep(accFull + acc, acc_ph, 1000);
             tc_fence_after();
-            const int co = tc.co_tile * 128 + q * 32 + lane;
+            const int co_base = tc.co_tile * 128 + q * 32;
+            const int co = co_base + lane;
             // part p = (phase, position tile) of the tile: its valid columns and the output row of its column 0
             auto part_geom = [&](int p, int& phase, int& m0, int& n_valid) {
                 phase = tc.phase + p / t_nts;
@@ -356,18 +415,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                         const float mean = n_valid > 0 ? sum / (float)n_valid : 0.f;
                         // pass 2: centred second moment + store
                         float m2 = 0.f;
-                        float* yrow = prm.y + ((size_t)b * pl.out_rows) * pl.out_ld + co;
+                        const size_t row_pitch = (size_t)pl.OS * pl.out_ld;
                         for (int c0 = 0; c0 < n_valid; c0 += 16) {
                             float v[16];
                             tmem_ld16(taddr + c0, v);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                if (c0 + i < n_valid) {
-                                    float d = v[i] - mean;
-                                    m2 += d * d;
-                                    const int row = (m0 + c0 + i) * pl.OS + phase;
-                                    yrow[(size_t)row * pl.out_ld] = v[i];
-                                }
+                            for (int i = 0; i < 16; ++i) if (c0 + i < n_valid) { const float d = v[i] - mean; m2 += d * d; }
+                            const size_t off0 = ((size_t)b * pl.out_rows + (size_t)(m0 + c0) * pl.OS + phase) * pl.out_ld + co_base;
+                            if (prm.scalar_raw_stores) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) if (c0 + i < n_valid) prm.y[off0 + (size_t)i * row_pitch + lane] = v[i];
+                            } else {
+                                store_f32(prm.y, off0, row_pitch, v, n_valid - c0);
                             }
                         }
                         if (prm.stats) {
@@ -416,12 +475,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
                             float v[16];
                             tmem_ld16(tclip + p * pl.n_tile + c0, v);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                if (c0 + i < n_valid) {
-                                    const int row = (m0 + c0 + i) * pl.OS + phase;
-                                    const float h = fmaf(v[i], sc, sh);
-                                    if (prm.dst0.dtype) bad_range |= store_act1(prm.dst0, b, row, co, h);
-                                    if (prm.dst1.dtype) bad_range |= store_act1(prm.dst1, b, row, co, h);
+                            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], sc, sh);
+                            const size_t row0 = (size_t)(m0 + c0) * pl.OS + phase;
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const ActDst& d = k ? prm.dst1 : prm.dst0;
+                                if (!d.dtype) continue;
+                                const size_t off0 = (size_t)b * d.batch_stride + row0 * d.ld + d.ch_off + co_base;
+                                if (d.dtype == PG_DT_F32) {
+                                    float a[16];
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) a[i] = leaky(v[i], d.slope);
+                                    store_f32(static_cast<float*>(d.hi), off0, (size_t)pl.OS * d.ld, a, n_valid - c0);
+                                } else {
+                                    store_split(d, off0, (size_t)pl.OS * d.ld, v, n_valid - c0);
                                 }
                             }
                         }
@@ -512,6 +579,8 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     PG_REQUIRE(n_terms < 2 || x_lo, "pg_conv_tc: activation lo plane required for this precision");
     PG_REQUIRE(d->C_in % 64 == 0 && d->C_out % 128 == 0, "pg_conv_tc: needs C_in %% 64 == 0 and C_out %% 128 == 0 (got %d, %d)", d->C_in, d->C_out);
     PG_REQUIRE(d->in_ld % 8 == 0, "pg_conv_tc: input row pitch must be a multiple of 8 elements");
+    PG_REQUIRE(d->tc_base_offset_mode == 0, "pg_conv_tc: descriptor base-offset mode 0 is the only supported one (the UMMA swizzle is a "
+               "function of the absolute shared-memory address: profiles/r01_tc_probe.log)");
     ConvTcParams prm;
     pg_conv_desc d_local = *d;
     if (const char* e = getenv("PG_TC_PAIR")) d_local.tc_cta_pair = atoi(e);   // A/B hook: 1 = single CTAs, 2 = require pairs
@@ -520,6 +589,7 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     int rc = conv_plan_build(d, &prm.plan);
     if (rc != PG_OK) return rc;
     const ConvPlan& pl = prm.plan;
+    { const char* e = getenv("PG_TC_SCALAR_STORES"); prm.scalar_raw_stores = e ? atoi(e) : 0; }
     prm.epi_mode = epi_mode; prm.gamma = nullptr; prm.beta = nullptr; prm.eps = 1e-5f; prm.ss_out = nullptr;
     if ((rc = to_act_dst(nullptr, 0, &prm.dst0, "pg_conv_tc", "dst0")) != PG_OK) return rc;
     prm.dst1 = prm.dst0;
@@ -529,7 +599,13 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
         if ((rc = to_act_dst(&epi->dst0, d->C_out, &prm.dst0, "pg_conv_tc", "dst0")) != PG_OK) return rc;
         if ((rc = to_act_dst(&epi->dst1, d->C_out, &prm.dst1, "pg_conv_tc", "dst1")) != PG_OK) return rc;
         PG_REQUIRE(prm.dst0.dtype || prm.dst1.dtype, "pg_conv_tc: fused epilogue without a destination");
+        for (const ActDst* a : {&prm.dst0, &prm.dst1})        // 128-bit stores of 8 (16-bit) / 4 (fp32) consecutive channels
+            PG_REQUIRE(!a->dtype || (a->ld % 8 == 0 && a->ch_off % 8 == 0 && a->batch_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a->hi) & 15) == 0 &&
+                                      (reinterpret_cast<uintptr_t>(a->lo) & 15) == 0),
+                       "pg_conv_tc: fused-epilogue destinations need 16-byte aligned planes and ld, ch_off, batch_stride multiples of 8");
         prm.gamma = epi->gamma; prm.beta = epi->beta; prm.eps = epi->eps; prm.ss_out = reinterpret_cast<float2*>(epi->scale_shift);
+    } else {
+        PG_REQUIRE(d->out_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "pg_conv_tc: y must be 16-byte aligned with out_ld a multiple of 4");
     }
     int g_sm_count, g_max_smem;
     device_limits(&g_sm_count, &g_max_smem);
@@ -543,7 +619,8 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     prm.b_slot_bytes = (pl.merged ? pl.mgroups : (pl.whole_clip ? pl.n_ntiles : 1)) * nb_cta * pl.strip_rows * 128;
     const int a_planes = n_terms == 3 ? 2 : 1, b_planes = n_terms >= 2 ? 2 : 1;
     // merged tiles read up to 15 rows past the last strip (junk columns only): 2 KB of slack keeps that inside the allocation
-    const int fixed = 2 * b_planes * prm.b_slot_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + (pl.merged ? 2048 : 0);
+    const int fixed = 2 * b_planes * prm.b_slot_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + 8192 /*epilogue staging tiles*/ +
+                      (pl.merged ? 2048 : 0);
     int nA = (g_max_smem - fixed) / (a_planes * kATileBytes);
     if (nA > kMaxASlots) nA = kMaxASlots;
     PG_REQUIRE(nA >= 2, "pg_conv_tc: strip of %d rows leaves no room for the weight ring", pl.strip_rows);

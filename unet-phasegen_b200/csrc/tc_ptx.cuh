@@ -170,6 +170,33 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, int base_off
     d |= (uint64_t)2 << 61;                                 // [61,64) SWIZZLE_128B
     return d;
 }
+// The same descriptors as two 32-bit words, for issue loops that only ever change the start address: the high word
+// (stride byte offset 1024, version 1, SWIZZLE_128B) is a constant, the low word is (address >> 4) [| LBO << 16] and
+// advancing the start address by n bytes is `lo += n >> 4` (no carry: shared-memory addresses are < 256 KB).
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) { return (saddr & 0x3FFFF) >> 4; }
+__device__ __forceinline__ uint32_t desc_lo_sw128_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ void umma_words(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128) : "memory");
+}
+__device__ __forceinline__ void umma_words_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128) : "memory");
+}
+
 // Instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, M = 128.
 __device__ __forceinline__ uint32_t make_idesc_bf16(int n, int m = 128) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);

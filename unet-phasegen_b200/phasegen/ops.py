@@ -215,6 +215,27 @@ def conv_stat_parts(desc):
     return p
 
 
+_PLAN_KEYS = ("n_tile", "n_ntiles", "nb", "strip_rows", "pair", "merged", "mgroups", "acc_stages", "n_chunks", "n_cotiles",
+              "OS", "IS", "taps0", "taps1", "groups0", "groups1", "whole_clip")
+
+
+def conv_plan(desc, whole_clip=None):
+    """Host-side tiling plan of pg_conv_tc for a layer (pg_conv_tc_plan) as a dict, plus `tiles` and `units` (persistent
+    CTAs or CTA pairs).  whole_clip: plan the whole-clip tiles of the fused per-clip norm epilogue; None if they do not fit."""
+    d = ConvDesc.from_buffer_copy(desc)
+    if whole_clip is not None:
+        d.tc_whole_clip = int(whole_clip)
+    out = (C.c_int * 17)()
+    if _lib.load().pg_conv_tc_plan(C.byref(d), out, 17) != 0:
+        return None
+    pl = dict(zip(_PLAN_KEYS, out))
+    slabs = pl["n_cotiles"] // 2 if pl["pair"] else pl["n_cotiles"]
+    parts = 1 if pl["whole_clip"] else pl["OS"] * pl["n_ntiles"]
+    pl["tiles"] = slabs * parts * -(-d.B // pl["nb"])
+    pl["units"] = 74 if pl["pair"] else 148
+    return pl
+
+
 def conv_simt(desc, x, w_simt, y):
     _lib.call("pg_conv_simt", C.byref(desc), _ptr(x), _ptr(w_simt), _ptr(y), _stream())
 

@@ -25,7 +25,7 @@ class _GraphedPipeline:
 
 class PhaseGenPipeline:
     def __init__(self, model, n_fft, hop, precision=None, per_clip=True, phase_only=True, normalize=True,
-                 fp16_overflow="raise"):
+                 fp16_overflow="raise", executor_kw=None):
         """fp16_overflow: what a checked call (check_finite=True) does when an activation left the fp16 range in one
         of the fp16 operand modes: "raise" (OverflowError) or "fallback" (re-run the batch with precision="bf16x3":
         bf16 planes have the fp32 range).  Unchecked calls leave the sticky flag for `range_overflow()`."""
@@ -35,6 +35,7 @@ class PhaseGenPipeline:
         self.model, self.n_fft, self.hop = model, n_fft, hop
         self.per_clip, self.phase_only, self.normalize = per_clip, phase_only, normalize
         self.precision, self.fp16_overflow = precision, fp16_overflow
+        self.executor_kw = dict(executor_kw or {})     # extra UNetExecutor options (e.g. fuse=False: the two-pass norm form)
         self._executors = []
         self._bad = None
 
@@ -49,7 +50,9 @@ class PhaseGenPipeline:
         B, N = wave.shape
         T = self.frames(N)
         prec = _precision or self.precision
-        kw = {"precision": prec} if prec else {}
+        kw = dict(self.executor_kw)
+        if prec:
+            kw["precision"] = prec
         ex = self.model.executor(B, T, wave.device, per_clip=self.per_clip, phase_only=self.phase_only, **kw)
         if not any(e is ex for e in self._executors):
             self._executors = (self._executors + [ex])[-8:]
@@ -134,7 +137,9 @@ class PhaseGenPipeline:
         import ctypes
         from . import _lib
         T = self.frames(n_samples)
-        kw = {"precision": self.precision} if self.precision else {}
+        kw = dict(self.executor_kw)
+        if self.precision:
+            kw["precision"] = self.precision
         ex = self.model.executor(B, T, device, per_clip=self.per_clip, phase_only=self.phase_only, **kw)
         out = (ctypes.c_int * 16)()
         if ex.prec == _lib.PG_PREC_FP32_SIMT or _lib.load().pg_conv_tc_plan(ctypes.byref(ex.up_desc[0]), out, 16) != 0:

@@ -211,7 +211,17 @@ class UNetExecutor:
         if not has_norm:
             return PG_EPI_ACT
         if self.per_clip and not self.use_running and ops.conv_epilogue_supported(desc, PG_EPI_NORM_ACT):
-            return PG_EPI_NORM_ACT
+            # whole-clip tiles are OS x n_ntiles times fewer: with a small batch (the batch-1 demo.py call) they would
+            # leave most of the persistent grid idle, and latency, not the normalising pass, is what counts there
+            # ... and a whole clip of more than 256 accumulator columns gives up the second TMEM stage: the epilogue
+            # (three passes over the accumulator) is then exposed instead of overlapped with the next tile's MMAs.
+            # Measured at the BASELINE shape (tools/pipe_ab.py): +0.45 ms on d2, +0.32 ms on u3 against 0.19 / 0.14 ms
+            # for their normalising pass, so a layer is fused only where its ordinary plan is single-stage anyway
+            # (the two-product layers) or the whole clip still fits two stages.
+            whole, split = ops.conv_plan(desc, whole_clip=1), ops.conv_plan(desc, whole_clip=0)
+            if whole is not None and (whole["tiles"] >= whole["units"] or whole["tiles"] >= split["tiles"]) and \
+                    whole["acc_stages"] >= split["acc_stages"]:
+                return PG_EPI_NORM_ACT
         return PG_EPI_RAW
 
     def check_range(self):
