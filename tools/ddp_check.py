@@ -12,7 +12,6 @@ all-gather of every rank's gradient, mean, Adam.  Checks, for the fp32-class and
   * the all-reduce + replicated-Adam form (shard_optimizer=False) agrees too;
   * the optimiser state round-trips through state_dict()/load_state_dict() on the sharded form.
 Prints one line per check and "DDP CHECK OK"; exits non-zero on failure."""
-import copy
 import os
 import sys
 
@@ -56,9 +55,8 @@ def main():
             torch.manual_seed(1000 + rank)                               # different initial weights per rank on purpose
             net = pg_model.UNetModel(C, 2 * C).to(dev)
             step = TrainStep(net, B, T, dev, precision=prec, grad_dtype=gdt, shard_optimizer=sharded)
-            ref = copy.deepcopy(net)                                     # after the broadcast: rank 0's weights everywhere
-            ref.__dict__["_exec"], ref.__dict__["_packed"] = {}, {}
-            ref.__dict__.pop("_pre_state_hook", None)
+            ref = pg_model.UNetModel(C, 2 * C).to(dev)                   # a purely local replica ...
+            ref.model.load_state_dict(net.model.state_dict())           # ... of the weights AFTER the broadcast (rank 0's everywhere)
             w0 = flat_params(net)
             first = [torch.empty_like(w0) for _ in range(world)]
             dist.all_gather(first, w0)

@@ -132,8 +132,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
             uint32_t n_it = 0;
             int st_i = 0; uint32_t st_ph = 0;
             const uint32_t idesc = (make_idesc_bf16_mn(prm.nci) & ~(0x1Fu << 24)) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);   // M = 256 for pairs
-            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc_flag) {
-                if (elect_one()) { if (PAIR) umma_bf16_pair(d, da, db, idesc, acc_flag); else umma_bf16(d, da, db, idesc, acc_flag); }
+            // descriptors as their low 32-bit words (tc_ptx.cuh): the issue loop only adds to start addresses
+            auto mma = [&](uint32_t d, uint32_t da, uint32_t db, uint32_t acc_flag) {
+                if (elect_one()) { if (PAIR) umma_words_pair(d, da, db, idesc, acc_flag); else umma_words(d, da, db, idesc, acc_flag); }
             };
             auto commit = [&](uint64_t* bar) {
                 if (elect_one()) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); }
@@ -152,22 +153,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t a_hi = st, a_lo = st + prm.a_plane;
                     const uint32_t b_hi = st + planes * prm.a_plane, b_lo = b_hi + prm.b_plane;
+                    const uint32_t aw_hi0 = desc_lo_sw128_mn(a_hi, lbo_a), aw_lo0 = desc_lo_sw128_mn(a_lo, lbo_a);
+                    const int n_ks = prm.R / 16;
                     for (int j = 0; j < grp.n_taps; ++j) {
                         const ConvTap tp = pl.taps[w.phase][grp.first_tap + j];
                         const uint32_t d_tmem = tmem_base + j * prm.nci;
-                        for (int ks = 0; ks < prm.R / 16; ++ks) {
+                        // 16 K rows further = 2048 B in both operands = +128 descriptor units
+                        uint32_t aw_hi = aw_hi0, aw_lo = aw_lo0;
+                        uint32_t bw_hi = desc_lo_sw128_mn(b_hi + (uint32_t)tp.shift * 128u, lbo_b);
+                        uint32_t bw_lo = desc_lo_sw128_mn(b_lo + (uint32_t)tp.shift * 128u, lbo_b);
+                        for (int ks = 0; ks < n_ks; ++ks, aw_hi += 128, aw_lo += 128, bw_hi += 128, bw_lo += 128) {
                             const uint32_t acc = (kc | ks) ? 1u : 0u;
-                            const uint32_t ao = (uint32_t)ks * 2048u, bo = ((uint32_t)tp.shift + (uint32_t)ks * 16u) * 128u;
-                            const uint64_t da_hi = make_desc_sw128_mn(a_hi + ao, lbo_a);
-                            const uint64_t db_hi = make_desc_sw128_mn(b_hi + bo, lbo_b);
                             if (three) {
-                                const uint64_t da_lo = make_desc_sw128_mn(a_lo + ao, lbo_a);
-                                const uint64_t db_lo = make_desc_sw128_mn(b_lo + bo, lbo_b);
-                                mma(d_tmem, da_lo, db_hi, acc);
-                                mma(d_tmem, da_hi, db_lo, 1);
-                                mma(d_tmem, da_hi, db_hi, 1);
+                                mma(d_tmem, aw_lo, bw_hi, acc);
+                                mma(d_tmem, aw_hi, bw_lo, 1);
+                                mma(d_tmem, aw_hi, bw_hi, 1);
                             } else {
-                                mma(d_tmem, da_hi, db_hi, acc);
+                                mma(d_tmem, aw_hi, bw_hi, acc);
                             }
                         }
                     }

@@ -193,7 +193,10 @@ class TrainStep:
             # replicas must start identical (DDP broadcasts at wrap time): parameters and norm buffers from rank 0
             with torch.no_grad():
                 for t in list(net.parameters()) + list(net.buffers()):
-                    dist.broadcast(t.data, 0)
+                    d = t.data
+                    if not d.is_contiguous():         # packed-storage conv weights: dense, permuted strides -> flat view of the storage
+                        d = d.as_strided((d.numel(),), (1,), d.storage_offset())
+                    dist.broadcast(d, 0)
             net.invalidate_packed()
         if grad_dtype is None:
             grad_dtype = "bf16" if precision == "bf16" else "fp32"
