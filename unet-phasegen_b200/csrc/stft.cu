@@ -50,10 +50,14 @@ template <int TG> struct FrameSync {
     }
 };
 
+// log1p|X| with two special-function instructions and no selects: sqrt.approx(0) = 0 needs no guard, and 1 + |X| >= 1 is
+// never subnormal, so lg2.approx needs none of the scaling __logf wraps around it (2 ulp each; the parity bound is 1e-4).
 __device__ __forceinline__ float fast_log1p_mag(float re, float im) {
     const float m2 = fmaf(re, re, im * im);
-    const float mag = m2 > 0.f ? m2 * rsqrtf(m2) : 0.f;
-    return __logf(1.0f + mag);
+    float mag, l2;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(m2));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(1.0f + mag));
+    return l2 * 0.693147180559945f;
 }
 
 // ------------------------------------------------------------------------------------ STFT
@@ -181,15 +185,11 @@ stft_kernel(const float* __restrict__ wave, int N, int T, const float2* __restri
 __device__ __forceinline__ cpx spec_value(float a, float p, int mode) {
     if (mode == PG_SPEC_CARTESIAN) return {a, p};
     float mag = a;
-    if (mode == PG_SPEC_POLAR_LOG) {                        // expm1 (demo.py:39)
-        mag = __expf(a) - 1.0f;
-        if (fabsf(a) < 0.03f) mag = a * fmaf(a, fmaf(a, fmaf(a, 1.f / 24.f, 1.f / 6.f), 0.5f), 1.0f);
-    }
-    // the predicted phase is an unbounded real (model.py: no tanh): reduce to [-pi, pi] before the fast sin/cos
-    const float n = rintf(p * 0.15915494309189535f);
-    float r = fmaf(n, -6.2831854820251465f, p);
-    r = fmaf(n, 1.7484555e-7f, r);
-    return {mag * __cosf(r), mag * __sinf(r)};
+    if (mode == PG_SPEC_POLAR_LOG) mag = __expf(a) - 1.0f;    // expm1 (demo.py:39): a = log1p|X| >= 0; the absolute error 1e-7 of
+                                                            // the plain form is invisible next to the bins that carry the signal
+    // sin.approx / cos.approx reduce their argument themselves (multiply by 1/2pi, hardware wrap): the phase of a
+    // normalised network output is a few radians, where this costs < 1e-6 absolute -- no Cody-Waite step needed
+    return {mag * __cosf(p), mag * __sinf(p)};
 }
 
 // FAST: mode == PG_SPEC_POLAR_LOG with a phase plane (the inference path), selection compiled in.
@@ -203,7 +203,7 @@ istft_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int
     using R = Radix<NC, true>;
     constexpr int FC = Cfg::FC, HOP = Cfg::HOP;
     extern __shared__ float2 smem2[];
-    float* wss_full = reinterpret_cast<float*>(smem2);      // [HOP] sum of w^2 over the 4 covering frames (16-byte aligned)
+    float* wss_full = reinterpret_cast<float*>(smem2);      // [HOP] 1 / sum of w^2 over the 4 covering frames (16-byte aligned)
     cpx* tabs = reinterpret_cast<cpx*>(wss_full + HOP);
     cpx* win = tabs + R::TOTAL;                             // synthesis Hann, (w[2m], w[2m+1])
     cpx* ring = win + NC;                                   // RING = FC + 3 windowed frames, slot = (frame - F0) mod RING
@@ -219,7 +219,7 @@ istft_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int
         float acc = 0.f;
 #pragma unroll
         for (int q = 0; q < 4; ++q) { const float wn = 0.5f - 0.5f * tw_g[q * HOP + i].x; acc += wn * wn; }
-        wss_full[i] = acc;
+        wss_full[i] = acc > 1.17549435e-38f ? 1.0f / acc : 1.0f;   // stored as the reciprocal: the overlap-add multiplies
     }
     const int b = blockIdx.y;
     if (b_ss) for (int m = tid; m < NC; m += kStftThreads) ss_tab[m] = __ldg(b_ss + (size_t)b * b_ss_stride + m);
@@ -280,7 +280,7 @@ istft_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int
             const int jb = lo + u / (HOP / 4), i = (u % (HOP / 4)) * 4;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), wss;
             const bool interior = jb >= 1 && jb + 2 < T;
-            if (interior) wss = *reinterpret_cast<const float4*>(wss_full + i);
+            if (interior) wss = *reinterpret_cast<const float4*>(wss_full + i);   // reciprocal of the window sum of squares
             else wss = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -295,11 +295,12 @@ istft_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int
                     wss.x += w0.x * w0.x; wss.y += w0.y * w0.y; wss.z += w1.x * w1.x; wss.w += w1.y * w1.y;
                 }
             }
+            if (!interior) {                                // edge blocks (two per clip): divide where > tiny (librosa)
+                wss.x = wss.x > 1.17549435e-38f ? 1.0f / wss.x : 1.0f; wss.y = wss.y > 1.17549435e-38f ? 1.0f / wss.y : 1.0f;
+                wss.z = wss.z > 1.17549435e-38f ? 1.0f / wss.z : 1.0f; wss.w = wss.w > 1.17549435e-38f ? 1.0f / wss.w : 1.0f;
+            }
             float4 y;
-            y.x = wss.x > 1.17549435e-38f ? acc.x / wss.x : acc.x;
-            y.y = wss.y > 1.17549435e-38f ? acc.y / wss.y : acc.y;
-            y.z = wss.z > 1.17549435e-38f ? acc.z / wss.z : acc.z;
-            y.w = wss.w > 1.17549435e-38f ? acc.w / wss.w : acc.w;
+            y.x = acc.x * wss.x; y.y = acc.y * wss.y; y.z = acc.z * wss.z; y.w = acc.w * wss.w;
             *reinterpret_cast<float4*>(wv + (size_t)jb * HOP + i) = y;
             const float mx = fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w)));
             if (!(mx <= 3.402823466e+38f) || y.x != y.x || y.y != y.y || y.z != y.z || y.w != y.w) bad = true;
