@@ -268,3 +268,57 @@ def test_fp16_range_guard_fires_in_every_writer():
     ops.conv_tc(d, xh, xl, hi, lo, None, None,
                 ops.conv_epilogue(PG_EPI_ACT, ops.act_dst(o_hi, o_lo, 16 * C_out, C_out, 0, PG_DT_F16_SPLIT, 0.0, flag)))
     assert int(flag.item()) == 1
+
+
+def test_kernels_write_only_inside_their_outputs():
+    """Own bounds check (compute-sanitizer is closed on this pool, profiles/r02_sanitizer_closed.log): every output of the
+    tensor-core / STFT / ISTFT kernels sits inside a larger sentinel-filled allocation; after the launch the guard regions
+    before and after the output, and the padding rows inside it, must be untouched."""
+    from phasegen import ops
+    from phasegen._lib import PG_SPEC_CARTESIAN, PG_STFT_REIM
+    SENT = 12345.0
+
+    def guarded(shape, dtype=torch.float32, pad=4096):
+        n = int(np.prod(shape))
+        buf = torch.full((n + 2 * pad,), SENT, device="cuda", dtype=dtype)
+        return buf, buf[pad:pad + n].view(*shape)
+
+    def intact(buf, n, pad=4096):
+        return bool((buf[:pad] == SENT).all()) and bool((buf[pad + n:] == SENT).all())
+
+    for layer, C, L_in, B, pair in (("u1", 128, 69, 3, 0), ("d2", 64, 349, 5, 1), ("u3", 128, 31, 5, 0)):
+        kind, k, s, p, C_in, C_out, rows, x, w = _case(layer, C, L_in, B, seed=9)
+        d = ops.conv_desc(kind, B, C_in, C_out, L_in, k, s, p, rows, C_in, ops.PG_PREC_BF16X3, taps_per_group=16, cta_pair=pair)
+        hi, lo, _ = ops.pack_weight(w, kind)
+        xh = x.to(torch.bfloat16); xl = (x - xh.float()).to(torch.bfloat16)
+        ybuf, y = guarded((B, d.L_out, C_out))
+        P = ops.conv_stat_parts(d)
+        sbuf, st = guarded((B, P, C_out, 4))
+        ops.conv_tc(d, xh, xl, hi, lo, y, st)
+        torch.cuda.synchronize()
+        assert intact(ybuf, y.numel()) and intact(sbuf, st.numel()), layer
+        assert not bool((y == SENT).any()), layer                     # ... and every element inside was written
+        # weight gradient of the same layer
+        grows = (d.L_out + 7) // 8 * 8
+        g = torch.zeros(B, grows, C_out, device="cuda"); g[:, :d.L_out] = torch.randn(B, d.L_out, C_out, device="cuda")
+        gh = g.bfloat16(); gl = (g - gh.float()).bfloat16()
+        wbuf, dw = guarded((k, C_out, C_in))
+        ops.wgrad_tc(d, xh, xl, gh, gl, grows, dw)
+        torch.cuda.synchronize()
+        assert intact(wbuf, dw.numel()) and not bool((dw == SENT).any()), layer
+    # STFT / ISTFT (library-allocated outputs are exact-size torch tensors: check through the C ABI with guarded buffers)
+    import ctypes as C_
+    from phasegen import _lib
+    n_fft, hop, T, B = 512, 128, 24, 3
+    N = (T - 1) * hop
+    wv = torch.randn(B, N, device="cuda") * 0.1
+    abuf, a = guarded((B, T, n_fft // 2)); bbuf, b = guarded((B, T, n_fft // 2))
+    _lib.call("pg_stft", ops._ptr(wv), B, N, n_fft, hop, ops._ptr(ops.twiddle(n_fft, wv.device)), PG_STFT_REIM, ops._ptr(a), ops._ptr(b),
+              None, None, 0, 0, ops._stream())
+    obuf, out = guarded((B, N))
+    pk = torch.zeros(B, device="cuda"); bad = torch.zeros(B, device="cuda", dtype=torch.int32)
+    _lib.call("pg_istft", ops._ptr(a), ops._ptr(b), PG_SPEC_CARTESIAN, B, T, n_fft, hop, ops._ptr(ops.twiddle(n_fft, wv.device)),
+              ops._ptr(out), ops._ptr(pk), ops._ptr(bad), None, 0, ops._stream())
+    torch.cuda.synchronize()
+    assert intact(abuf, a.numel()) and intact(bbuf, b.numel()) and intact(obuf, out.numel())
+    assert not bool((a == SENT).any()) and not bool((out == SENT).any())
