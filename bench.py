@@ -154,7 +154,7 @@ class Dist:
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_step(n_clips, seed=0, time_budget_s=None):
+def cpu_reference_step(n_clips, seed=0, time_budget_s=None, mkldnn=False):
     """The reference's CPU path (oracle port: numpy STFT/ISTFT restating librosa + the reference
     U-Net arithmetic through torch CPU fp32 with oneDNN off, batch 1 per clip like demo.py:33-42)
     on `n_clips` clips of the bench workload.  Returns (seconds, clips done)."""
@@ -172,7 +172,7 @@ def cpu_reference_step(n_clips, seed=0, time_budget_s=None):
     for i in range(n_clips):
         S = stft_np.stft(waves[i], N_FFT, HOP)[1:]
         lm = np.log1p(np.abs(S)).astype(np.float32)
-        out = unet_torch.unet_forward(sd, torch.from_numpy(lm)[None], torch.float32, per_clip_bn=True)[0].numpy()
+        out = unet_torch.unet_forward(sd, torch.from_numpy(lm)[None], torch.float32, per_clip_bn=True, mkldnn=mkldnn)[0].numpy()
         stft_np.generate_audio(stft_np.polar_to_complex(lm, out[:C]), SR, HOP, is_stft=True)
         done += 1
         if time_budget_s is not None and time.perf_counter() - t0 > time_budget_s:
@@ -195,6 +195,10 @@ def run_reference(args):
         times.append(dt / done)
     per_clip = statistics.mean(times)
     value = clip_s / per_clip
+    # the stock oneDNN-on time, for context only -- its fp32 transposed convolution is ~22 % wrong in
+    # this image, so it is NOT a valid baseline
+    cpu_reference_step(1, mkldnn=True)
+    dt_on, done_on = cpu_reference_step(n, mkldnn=True)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_clip * n * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -204,6 +208,8 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{n} clips per step x {args.steps} steps, oracle port (numpy STFT/ISTFT + torch-CPU fp32 U-Net, oneDNN off)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "onednn_on_numerically_invalid": {"value": clip_s * done_on / dt_on, "unit": UNIT,
+                                              "note": "same loop with oneDNN enabled; its k5/s2 transposed convolution is ~22 % wrong here: context only, not a baseline"},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 

@@ -52,14 +52,15 @@ def _apply(name, x, sd, per_clip, dt):
     return _bn_train(y, sd, nkey, per_clip, dt) if nkey else y
 
 
-def unet_forward(sd, x, dtype=torch.float64, per_clip_bn=False, taps=None, grad=False):
+def unet_forward(sd, x, dtype=torch.float64, per_clip_bn=False, taps=None, grad=False, mkldnn=False):
     """x [B,C,T] -> [B,2C,T]; out[:, :C] is the raw phase estimate, out[:, C:] the log-mag
     estimate (train.py:45).  ``taps`` (a dict) receives the raw conv outputs and the
     normalised tensors of every layer for per-layer parity checks.  ``grad=True`` keeps the
-    autograd graph (used by ``loss_and_grads``)."""
+    autograd graph (used by ``loss_and_grads``).  ``mkldnn=True`` leaves oneDNN on: only for TIMING the stock CPU path
+     -- its fp32 result is numerically invalid in this image (module docstring)."""
     dt = dtype
     lrelu = lambda t: F.leaky_relu(t, 0.2)
-    with torch.set_grad_enabled(grad), torch.backends.mkldnn.flags(enabled=False):
+    with torch.set_grad_enabled(grad), torch.backends.mkldnn.flags(enabled=bool(mkldnn)):
         x = x.to(dt)
         y1 = _apply("d1", x, sd, per_clip_bn, dt)                      # model.py:90, no norm
         h2 = _apply("d2", lrelu(y1), sd, per_clip_bn, dt)              # model.py:103

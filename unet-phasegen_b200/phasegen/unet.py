@@ -25,7 +25,7 @@ input buffer, never a copy.  Per layer one of three forms (PG_EPI_*, include/pha
 import torch
 
 from . import ops
-from ._lib import (PG_CONV, PG_CONV_TRANSPOSE, PG_DT_BF16, PG_DT_BF16_SPLIT, PG_DT_F16_SPLIT, PG_DT_F32, PG_EPI_ACT,
+from ._lib import (PG_CONV, PG_CONV_TRANSPOSE, PG_DT_BF16, PG_DT_BF16_SPLIT, PG_DT_F16, PG_DT_F16_SPLIT, PG_DT_F32, PG_EPI_ACT,
                    PG_EPI_NORM_ACT, PG_EPI_RAW, PG_PREC_BF16, PG_PREC_BF16X3, PG_PREC_F16, PG_PREC_F16X2, PG_PREC_F16X3,
                    PG_PREC_FP32_SIMT, PRECISIONS)
 
@@ -85,6 +85,10 @@ class _Operand:
         if prec == PG_PREC_FP32_SIMT:
             self.dtype = PG_DT_F32
             self.hi = torch.zeros(B, self.rows, ld, device=device, dtype=torch.float32)
+            self.lo = None
+        elif prec == PG_PREC_F16:                      # consumed by a single-product layer: the lo plane is never read
+            self.dtype = PG_DT_F16
+            self.hi = torch.zeros(B, self.rows, ld, device=device, dtype=torch.float16)
             self.lo = None
         elif prec in _F16_PRECS:
             self.dtype = PG_DT_F16_SPLIT
@@ -166,7 +170,9 @@ class UNetExecutor:
                 raise RuntimeError(f"phasegen: level {i} down conv expects {lv.down.C_in} channels, gets {src.ld}")
             self.a[i] = _Operand(B, Lz, lv.down.C_out, prec, dev, rf)   # LeakyReLU(h_i)  /  ReLU(z) innermost
             if i < D - 1:
-                self.cat[i] = _Operand(B, Lz, lv.up.C_in, prec, dev, rf)  # [ReLU(h_i) | ReLU(n_{i+1})]
+                # [ReLU(h_i) | ReLU(n_{i+1})], read by up conv i only: planes follow that layer's precision
+                cat_prec = PG_PREC_F16 if self.layer_prec("u", i) == PG_PREC_F16 else prec
+                self.cat[i] = _Operand(B, Lz, lv.up.C_in, cat_prec, dev, rf)
                 if lv.down.C_out + levels[i + 1].up.C_out != lv.up.C_in:
                     raise RuntimeError(f"phasegen: level {i}: concat width {lv.down.C_out}+{levels[i + 1].up.C_out} "
                                        f"!= up conv input {lv.up.C_in}")
