@@ -413,11 +413,24 @@ def longform_leg(args, D, net):
     y = out[0]
     finite = bool(torch.isfinite(y).all())
     peak = float(y.abs().max())
+    # parity at full scale, measured here: (1) windows of the recording through the plain batch-1 pipeline call (the
+    # demo.py:33-42 semantics) against the same windows inside this rank's long-form batch; (2) the stitch kernel on
+    # all-ones windows over the full 297-window span must return exactly one everywhere (the cross-fade gains sum to one)
+    wins, idx = longform.cut_windows(wave, HOP, T, D.rank, D.world)
+    batch_out = pipe(wins.contiguous()).clone()
+    worst = 0.0
+    for j in sorted({0, len(idx) // 2, len(idx) - 1}):
+        single = pipe(wins[j:j + 1].contiguous())
+        worst = max(worst, float((single[0] - batch_out[j]).norm() / batch_out[j].norm()))
+    ones = longform.stitch(torch.ones(n_win, win, device=D.dev), list(range(n_win)), n_win, n_total, HOP, T)
+    ones_dev = float((ones - 1).abs().max())
     return {"metric": "longform_audio_seconds_per_second", "value": n_total / SR / (ms / 1e3), "unit": UNIT, "n_gpus": D.world,
             "ms_per_recording": ms, "scaling": "strong", "windows": n_win, "windows_per_rank": -(-n_win // D.world),
             "workload": f"{minutes:g}-minute recording ({n_total} samples), {n_win} windows of {T} frames, step {step} samples, "
                         f"round-robin over {D.world} rank(s), {prec}; cut + pipeline + all-gather + pg_stitch + global peak normalise",
-            "finite": finite, "peak_after_normalise": peak}
+            "finite": finite, "peak_after_normalise": peak,
+            "checks": {"windows_vs_batch1_pipeline_rel_l2": worst, "stitch_of_ones_max_dev": ones_dev,
+                       "pass": bool(finite and worst < 1e-4 and ones_dev < 1e-5)}}
 
 
 # ------------------------------------------------------------------------------------------ GPU library arm
