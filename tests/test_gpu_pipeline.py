@@ -279,3 +279,33 @@ def test_fp16_range_guard_raises_or_falls_back():
     ok = PhaseGenPipeline(model.UNetModel(C, 2 * C).cuda(), n_fft, hop, precision="f16mix", per_clip=True, phase_only=True)
     ok(wave, check_finite=True)                             # ordinary weights: no flag
     assert not ok.range_overflow()
+
+
+def test_stitch_kernel_matches_host_form_and_round_robin_layout():
+    """pg_stitch against the float64 host form of the same cross-fade, and its multi-rank input layout: windows dealt
+    round-robin to W ranks and all-gathered (window i at slot (i mod W) * per_rank + i div W, ragged last round zero)
+    stitch to exactly what the plain order gives; the peak output feeds one global normalisation."""
+    from phasegen import longform
+    hop, frames = 64, 40
+    win, step, _ = longform.window_plan(10 ** 6, hop, frames)
+    n = 11
+    N = win + (n - 1) * step - 37                              # ragged tail
+    g = torch.Generator().manual_seed(61)
+    wins = torch.randn(n, win, generator=g)
+    ref = longform.stitch(wins, list(range(n)), n, N, hop, frames)                       # host form (float64 accumulate)
+    peak = torch.zeros(1, device="cuda")
+    got = longform.stitch(wins.cuda(), list(range(n)), n, N, hop, frames, peak_out=peak)
+    assert got.shape == (N,) and float((got.cpu() - ref).abs().max()) < 2e-6
+    assert abs(float(peak) - float(ref.abs().max())) < 1e-5
+    for W in (2, 3, 8):
+        per_rank = -(-n // W)
+        gathered = torch.zeros(W * per_rank, win)
+        for i in range(n):
+            gathered[(i % W) * per_rank + i // W] = wins[i]
+        rr = longform.stitch(gathered.cuda(), list(range(n)), n, N, hop, frames, world=W, per_rank=per_rank)
+        assert torch.equal(rr, got), W
+        assert float((longform.stitch(gathered, list(range(n)), n, N, hop, frames, world=W, per_rank=per_rank) - ref).abs().max()) == 0
+    with pytest.raises(RuntimeError, match="step must lie"):
+        from phasegen import _lib, ops
+        o = torch.zeros(100, device="cuda")
+        _lib.call("pg_stitch", ops._ptr(wins.cuda()), 2, 100, 30, 1, 2, ops._ptr(o), 100, None, ops._stream())
