@@ -173,7 +173,8 @@ def test_conv_argument_errors():
 @pytest.mark.parametrize("layer,C,L_in,B,pair", [
     ("d1", 128, 696, 5, 0), ("d4", 128, 171, 7, 0), ("d1", 64, 136, 3, 1),                      # no norm: PG_EPI_ACT
     ("d2", 128, 349, 5, 0), ("d3", 128, 346, 5, 0), ("u4", 128, 171, 5, 0), ("u3", 128, 171, 5, 0), ("u2", 128, 346, 5, 0),
-    ("u2", 64, 346, 3, 1), ("u3", 64, 171, 6, 1), ("d3", 128, 66, 9, 0), ("u4", 128, 135, 9, 0), ("d2", 128, 69, 7, 0)])
+    ("u2", 64, 346, 3, 1), ("u3", 64, 171, 6, 1), ("d3", 128, 66, 9, 0), ("u4", 128, 135, 9, 0), ("d2", 128, 69, 7, 0),
+    ("u3", 128, 121, 5, 0)])                                    # two phases x 128 columns: two clips per whole-clip tile (f16x2)
 def test_tc_conv_fused_epilogues(layer, C, L_in, B, pair, prec):
     """The fused epilogues (PG_EPI_ACT; PG_EPI_NORM_ACT with whole-clip tiles: two position tiles, two output phases,
     merged short clips, CTA pairs and single CTAs) against the two-pass form built from the exact SIMT convolution:

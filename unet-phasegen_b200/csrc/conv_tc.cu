@@ -59,7 +59,6 @@ struct ConvTcParams {
     const float* gamma; const float* beta; float eps;
     ActDst dst0, dst1;
     float2* ss_out;                 // NORM_ACT: optional [B][C_out] (scale, shift) record of what was applied
-    int scalar_raw_stores;          // A/B hook (PG_TC_SCALAR_STORES=1): RAW epilogue stores one fp32 per thread instead of staging
 };
 // plan.pair = 1: tiles are 256 output channels wide and owned by a CTA pair; plan.strip_rows is then the
 // HALF strip each CTA loads (n_tile/2 + largest shift rows).
@@ -422,12 +421,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
 #pragma unroll
                             for (int i = 0; i < 16; ++i) if (c0 + i < n_valid) { const float d = v[i] - mean; m2 += d * d; }
                             const size_t off0 = ((size_t)b * pl.out_rows + (size_t)(m0 + c0) * pl.OS + phase) * pl.out_ld + co_base;
-                            if (prm.scalar_raw_stores) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) if (c0 + i < n_valid) prm.y[off0 + (size_t)i * row_pitch + lane] = v[i];
-                            } else {
-                                store_f32(prm.y, off0, row_pitch, v, n_valid - c0);
-                            }
+                            store_f32(prm.y, off0, row_pitch, v, n_valid - c0);
                         }
                         if (prm.stats) {
                             const int P = pl.OS * pl.n_ntiles;
@@ -589,7 +583,6 @@ extern "C" int pg_conv_tc(const pg_conv_desc* d, const uint16_t* x_hi, const uin
     int rc = conv_plan_build(d, &prm.plan);
     if (rc != PG_OK) return rc;
     const ConvPlan& pl = prm.plan;
-    { const char* e = getenv("PG_TC_SCALAR_STORES"); prm.scalar_raw_stores = e ? atoi(e) : 0; }
     prm.epi_mode = epi_mode; prm.gamma = nullptr; prm.beta = nullptr; prm.eps = 1e-5f; prm.ss_out = nullptr;
     if ((rc = to_act_dst(nullptr, 0, &prm.dst0, "pg_conv_tc", "dst0")) != PG_OK) return rc;
     prm.dst1 = prm.dst0;

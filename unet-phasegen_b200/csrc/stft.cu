@@ -64,7 +64,7 @@ __device__ __forceinline__ float fast_log1p_mag(float re, float im) {
 // FAST = 0: every output selected at run time.  FAST = 1 / 2: the inference path (log-magnitude fp32 plane +
 // bf16 / fp16 hi,lo operand planes, no phase plane) with the selection compiled in.
 template <int NC, int FAST>
-__global__ void __launch_bounds__(kStftThreads)
+__global__ void __launch_bounds__(kStftThreads, 3)          // 3 CTAs per SM (<= 85 registers): the kernel is issue/latency-bound
 stft_kernel(const float* __restrict__ wave, int N, int T, const float2* __restrict__ tw_g, int mode,
             float* __restrict__ out_a, float* __restrict__ out_b,
             uint16_t* __restrict__ op_hi, uint16_t* __restrict__ op_lo,

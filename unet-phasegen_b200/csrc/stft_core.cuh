@@ -204,19 +204,27 @@ PG_HD void fwd_fused_last_512(const cpx* s, int t, const cpx* tabs, Emit&& emit)
         const cpx tp = cmul(w, p1), tq = cmul(wq, q1);
         const cpx zk = cadd(p0, tp), zk2 = csub(p0, tp);      // Z[k], Z[k+256]
         const cpx zq = cadd(q0, tq), zq2 = csub(q0, tq);      // Z[kq], Z[kq+256]
-        cpx xa, xb;
-        if (k != 0) {
-            herm_post(zk, zq2, up[k], xa, xb);                // pair (k, 512-k): 512-k = kq+256
-            emit(k, xa); emit(512 - k, xb);
-            herm_post(zq, zk2, up[kq], xa, xb);               // pair (256-k, 256+k)
-            emit(kq, xa); emit(k + 256, xb);
+        // General item: pairs (k, 512-k) = (Z[k], Z[kq+256]) and (256-k, 256+k) = (Z[kq], Z[k+256]).  Item k = 0 owns
+        // {128, 256, 384, 512}: DC/Nyquist from (Z[0], Z[0]), bin 256 from (Z[256], Z[256]), pair (128, 384) from
+        // (Z[128], Z[384]).  Selects instead of a divergent branch (see inv_fused_first_512); the third pair and the
+        // bin selects exist in the first item only.
+        const bool z0 = (i == 0) && (k == 0);
+        cpx a1 = zq2, b1 = zk2;
+        if (i == 0) { a1 = z0 ? zk : zq2; b1 = z0 ? zq2 : zk2; }
+        cpx xa, xb, ya, yb;
+        herm_post(zk, a1, up[k], xa, xb);                     // k = 0: (Z[0], Z[0], up[0]) -> xb = X[512]
+        herm_post(zq, b1, up[kq], ya, yb);                    // k = 0: (Z[128], Z[384], up[128]) -> X[128], X[384]
+        if (i == 0) {
+            cpx ma, mb;
+            herm_post(zk2, zk2, up[256], ma, mb);             // bin 256 (self-mirrored), used by item 0 only
+            // bins: general {k, 512-k, kq, k+256}; item 0 {256, 512, 128, 384}
+            emit(z0 ? 256 : k, z0 ? ma : xa);
+            emit(512 - k, xb);
+            emit(kq, ya);
+            emit(z0 ? 384 : k + 256, yb);
         } else {
-            herm_post(zk, zk, up[0], xa, xb);                 // a = 0: DC (dropped) and Nyquist
-            emit(512, xb);
-            herm_post(zk2, zk2, up[256], xa, xb);             // a = 256 (self-mirrored)
-            emit(256, xa);
-            herm_post(zq, zq2, up[128], xa, xb);              // pair (128, 384)
-            emit(128, xa); emit(384, xb);
+            emit(k, xa); emit(512 - k, xb);
+            emit(kq, ya); emit(k + 256, yb);
         }
     }
 }
@@ -272,15 +280,25 @@ PG_HD void inv_fused_first_512(cpx* s, int t, const cpx* tabs, float scale, cons
         const int kq = k == 0 ? 128 : 256 - k;
         cpx zk, zk2, zq, zq2;                                 // Z[k], Z[k+256], Z[kq], Z[kq+256]
         const cpx x0 = x[4 * i], x1 = x[4 * i + 1], x2 = x[4 * i + 2], x3 = x[4 * i + 3];   // order: inv_bin<512>
-        if (k != 0) {
-            herm_pre(x0, x1, up[k], scale, zk, zq2);          // X[k], X[512-k]
-            herm_pre(x2, x3, up[kq], scale, zq, zk2);         // X[256-k], X[256+k]
-        } else {
-            cpx xn = x0; xn.y = 0.f;                          // X[512]
-            cpx dummy;
-            herm_pre(cpx{0.f, 0.f}, xn, up[0], scale, zk, dummy);
-            herm_pre(x1, x1, up[256], scale, zk2, dummy);     // X[256]
-            herm_pre(x2, x3, up[128], scale, zq, zq2);        // X[128], X[384]
+        // General item: (X[k], X[512-k]) -> (Z[k], Z[kq+256]) and (X[256-k], X[256+k]) -> (Z[kq], Z[k+256]).
+        // Item k = 0 (thread 0, i = 0) owns {X[512], X[256], X[128], X[384]} instead and needs a third pair.  It is
+        // handled with selects, not a branch: a divergent lane 0 made every warp walk both code paths (the ISTFT spent
+        // ~70 of its 1,956 instructions per frame on the reconvergence alone); only i = 0 pays for the extra pair.
+        const bool z0 = (i == 0) && (k == 0);
+        cpx a0 = x0, a1 = x1;
+        if (i == 0) {                                         // compile-time: the selects exist in the first item only
+            a0 = z0 ? cpx{0.f, 0.f} : x0;                     // X[0] = 0 (utils.py:38-39)
+            a1 = z0 ? cpx{x0.x, 0.f} : x1;                    // X[512], imaginary part ignored like numpy's irfft
+        }
+        cpx pa, pb, qa, qb;
+        herm_pre(a0, a1, up[k], scale, pa, pb);               // k = 0: up[0], pa = Z[0]
+        herm_pre(x2, x3, up[kq], scale, qa, qb);              // k = 0: (X[128], X[384]) -> (Z[128], Z[384])
+        zk = pa; zq = qa; zq2 = pb; zk2 = qb;
+        if (i == 0) {
+            cpx ma, mb;
+            herm_pre(x1, x1, up[256], scale, ma, mb);         // X[256] (self-mirrored) -> Z[256]
+            zq2 = z0 ? qb : pb;
+            zk2 = z0 ? ma : qb;
         }
         s[pad2(2 * k)] = cadd(zk, zk2);
         s[pad2(2 * k + 1)] = csub(zk, zk2);

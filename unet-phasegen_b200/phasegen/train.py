@@ -274,6 +274,14 @@ class TrainStep:
                                f"{(ex.B, ex.T, ex.levels[0].down.C_in)}, got {tuple(logmag_cl.shape)} / {tuple(phase_cl.shape)}")
         net._ensure_packed(ex)
         if self.sharded is not None:
+            # a re-pack (weights changed outside this object) allocates new operand planes: re-bind the shards to them
+            for it in self.items:
+                if "sh" in it:
+                    which, i = it["conv"]
+                    hi, lo = (ex.wd[i] if which == "dn" else ex.wu[i])[:2]
+                    if id(hi) != it["planes"]:
+                        it["sh"].planes = [pl.view(-1) for pl in (hi, lo) if pl is not None]
+                        it["planes"] = id(hi)
             # each layer's refreshed planes are awaited right before the first kernel that reads them
             pending = {it["planes"]: it["key"] for it in self.items if "sh" in it}
 
