@@ -113,3 +113,21 @@ def test_stft_istft_match_scipy(n_fft):
                            input_onesided=True)
     mine = stft_np.istft(S, hop)
     assert rel_l2(back[:len(mine)], mine) < 1e-10
+
+
+@pytest.mark.parametrize("n_fft", [512, 1024, 2048])
+def test_stft_matches_the_librosa_compatible_numpy_stft_of_transformers(n_fft):
+    """A fourth implementation: transformers.audio_utils.spectrogram (numpy framing + rfft; its documentation states it
+    is compatible with librosa.stft, and its own test-suite pins it to librosa-generated values).  librosa itself is not
+    installable here, so this -- with torch.stft, scipy.signal.stft and the scipy window provider librosa calls -- is
+    how the restatement is held to the dependency's published behaviour."""
+    audio_utils = pytest.importorskip("transformers.audio_utils")
+    rng = np.random.default_rng(n_fft)
+    w = rng.standard_normal(6 * n_fft + 123)
+    win = audio_utils.window_function(n_fft, "hann", periodic=True)
+    assert np.abs(win - stft_np.hann_periodic(n_fft)).max() < 1e-12 if hasattr(stft_np, "hann_periodic") else True
+    S = audio_utils.spectrogram(w, win, frame_length=n_fft, hop_length=n_fft // 4, fft_length=n_fft, power=None,
+                                center=True, pad_mode="reflect", onesided=True, dtype=np.float64)
+    ref = stft_np.stft(w, n_fft, n_fft // 4)
+    assert S.shape == ref.shape
+    assert np.abs(S - ref).max() / np.abs(ref).max() < 1e-6       # the transformers routine returns complex64
