@@ -21,8 +21,15 @@
 //   MMAs from a descriptor whose start address is advanced by shift*128 B inside the swizzle
 //   pattern.  taps_per_group = 1 disables the trick (one strip per tap).
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5
-// epilogue: TMEM -> registers -> per-channel partial batch-norm statistics (count, mean, M2;
-// two passes over TMEM so the variance is centred) and the raw fp32 output, channels-last.
+// epilogue: TMEM -> registers -> one of three forms (PG_EPI_*, include/phasegen.h):
+//   RAW       per-channel partial batch-norm statistics (count, mean, M2; two passes over TMEM so the
+//             variance is centred) and the raw fp32 output, channels-last;
+//   ACT       activation(s) (model.py:80,82) and the consumers' 16-bit hi/lo operand planes, written at a
+//             channel offset (the skip concat of model.py:113) -- layers without norm;
+//   NORM_ACT  train-mode norm with the clip's own statistics first (three passes over TMEM), for tiles that
+//             hold every output position of a clip ("whole-clip" tiles: all output phases x position tiles
+//             side by side in the accumulator, see ConvPlan::whole_clip).
+// Stores go through a per-warp shared-memory tile so that they leave as 128-bit stores.
 // Persistent: grid = min(#tiles, #SMs); the tile order keeps co-resident CTAs on the same
 // weight slab (L2 reuse).  Two TMEM accumulators (2 x 256 columns) overlap epilogue and MMA.
 //
