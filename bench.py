@@ -507,7 +507,7 @@ def main():
     D = Dist()
     world, rank, dev = D.world, D.rank, D.dev
     if args.workload == "train":
-        line = train_leg(args, D, with_library_baseline=True)
+        line = train_leg(args, D, with_library_baseline=not args.no_extras)
         if rank == 0:
             print(json.dumps(line), flush=True)
         D.close()

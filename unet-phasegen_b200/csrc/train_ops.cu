@@ -9,6 +9,8 @@
 //   * pg_wgrad_simt     exact-fp32 weight gradient (small channel counts, GPU-side check of wgrad_tc)
 //   * pg_unpack_grad    packed [k][C_out][C_in] gradient -> torch Conv / ConvT weight layout
 //   * pg_adam_step      torch.optim.Adam defaults (train.py:26-27), fused, fp32 state
+#include <cstdlib>
+
 #include "common.cuh"
 #include "conv_plan.h"
 
@@ -226,30 +228,32 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
                         reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
                       ((reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo)) & 7) == 0 ? n / 4 : 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        float4 pi = reinterpret_cast<float4*>(p)[i];
+        // streaming (evict-first) accesses: 28 B/parameter pass through once; they should not push the tensor-core kernels'
+        // weight slabs and activations out of L2 when the update runs beside them (one-GPU overlap, phasegen/train.py)
+        float4 pi = __ldcs(reinterpret_cast<const float4*>(p) + i);
         float4 gi;
         if (g_bf16) {
-            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(g16) + i);
+            const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(g16) + i);
             const float2 lo2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
             const float2 hi2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
             gi = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
         } else {
-            gi = __ldg(reinterpret_cast<const float4*>(g) + i);
+            gi = __ldcs(reinterpret_cast<const float4*>(g) + i);
         }
-        float4 mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i];
+        float4 mi = __ldcs(reinterpret_cast<const float4*>(m) + i), vi = __ldcs(reinterpret_cast<const float4*>(v) + i);
         adam_one(pi.x, gi.x, mi.x, vi.x, lr_bc1, b1, b2, eps, bc2_sqrt_inv, grad_scale);
         adam_one(pi.y, gi.y, mi.y, vi.y, lr_bc1, b1, b2, eps, bc2_sqrt_inv, grad_scale);
         adam_one(pi.z, gi.z, mi.z, vi.z, lr_bc1, b1, b2, eps, bc2_sqrt_inv, grad_scale);
         adam_one(pi.w, gi.w, mi.w, vi.w, lr_bc1, b1, b2, eps, bc2_sqrt_inv, grad_scale);
-        reinterpret_cast<float4*>(p)[i] = pi;
-        reinterpret_cast<float4*>(m)[i] = mi;
-        reinterpret_cast<float4*>(v)[i] = vi;
+        __stcs(reinterpret_cast<float4*>(p) + i, pi);
+        __stcs(reinterpret_cast<float4*>(m) + i, mi);
+        __stcs(reinterpret_cast<float4*>(v) + i, vi);
         if (w_hi) {
             __align__(8) uint16_t h[4], l[4];
             split16(pi.x, PG_FMT_BF16, h[0], l[0]); split16(pi.y, PG_FMT_BF16, h[1], l[1]);
             split16(pi.z, PG_FMT_BF16, h[2], l[2]); split16(pi.w, PG_FMT_BF16, h[3], l[3]);
-            reinterpret_cast<uint2*>(w_hi)[i] = *reinterpret_cast<uint2*>(h);
-            if (w_lo) reinterpret_cast<uint2*>(w_lo)[i] = *reinterpret_cast<uint2*>(l);
+            __stcs(reinterpret_cast<uint2*>(w_hi) + i, *reinterpret_cast<uint2*>(h));
+            if (w_lo) __stcs(reinterpret_cast<uint2*>(w_lo) + i, *reinterpret_cast<uint2*>(l));
         }
     }
     for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -338,6 +342,7 @@ extern "C" int pg_adam_step(float* p, const void* g, int g_dtype, float* m, floa
     const float bc1 = 1.f - powf(beta1, (float)step);
     const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
     int gx = (int)((n / 4 + 255) / 256); if (gx > 148 * 16) gx = 148 * 16; if (gx < 1) gx = 1;
+    if (const char* e = getenv("PG_ADAM_MAX_CTAS")) { const int cap = atoi(e); if (cap > 0 && gx > cap) gx = cap; }   // experiment hook
     adam_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, static_cast<const float*>(g), m, v, (size_t)n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale, w_hi, w_lo, g_dtype == PG_DT_BF16 ? 1 : 0);
     return check_launch("adam_kernel");
 }
