@@ -212,83 +212,3 @@ def test_istft_run_boundaries(n_fft, hop, T):
         assert wv.shape[1] == ref.shape[0]
         assert rel_l2(wv[b].cpu().numpy(), ref) < 2e-5
         assert abs(float(peak[b]) - np.abs(ref).max()) < 1e-4 * np.abs(ref).max()
-
-
-def _with_pair(flag, fn):
-    """Run fn with the n_fft-1024 frame-pair kernels on (flag=1) or off (0: the one-frame-per-warp kernels)."""
-    import os
-    old = os.environ.get("PG_STFT_PAIR")
-    os.environ["PG_STFT_PAIR"] = str(flag)
-    try:
-        return fn()
-    finally:
-        if old is None:
-            os.environ.pop("PG_STFT_PAIR", None)
-        else:
-            os.environ["PG_STFT_PAIR"] = old
-
-
-@pytest.mark.parametrize("fmt", ["f16", "bf16"])
-def test_stft_frame_pair_kernel_matches_oracle_and_scalar_kernel(fmt):
-    """The inference form of the STFT at n_fft 1024 (fp32 log-magnitude plane + hi/lo operand planes) runs two frames
-    per warp on packed fp32x2 arithmetic (csrc/stft_pair.cuh).  Checked against the float64 oracle and against the
-    one-frame-per-warp kernel on: odd frame counts (the last pair has one live frame), the shortest legal clip, clips
-    whose edge frames reflect on both sides, an unaligned base pointer, and a batch with several CTAs per clip."""
-    from phasegen import ops
-    n_fft, hop, C = 1024, 256, 512
-    rng = np.random.default_rng(5)
-    dt = torch.float16 if fmt == "f16" else torch.bfloat16
-    for N, B, off in ((n_fft // 2 + 1, 2, 0), (5 * hop + 37, 3, 0), (70 * hop, 2, 0), (66 * hop + 1, 2, 1), (695 * hop, 2, 0)):
-        w = (0.5 * rng.standard_normal((B, N))).astype(np.float32)
-        flat = torch.zeros(B * N + 1, device="cuda")
-        wave = flat[off:off + B * N].view(B, N)
-        wave.copy_(torch.from_numpy(w))
-        T = 1 + N // hop
-        rows = (T + 7) // 8 * 8
-
-        def run():
-            hi = torch.zeros(B, rows, C, device="cuda", dtype=dt)
-            lo = torch.zeros_like(hi)
-            lm, _ = ops.stft(wave, n_fft, hop, ops.PG_STFT_LOGMAG, want_second=False, operand=(hi, lo, rows * C))
-            torch.cuda.synchronize()
-            return lm, hi, lo
-        lm, hi, lo = _with_pair(1, run)
-        lm0, hi0, lo0 = _with_pair(0, run)
-        for b in range(B):
-            S = stft_np.stft(w[b], n_fft, hop)[1:]
-            ref = np.log1p(np.abs(S)).T
-            assert rel_l2(lm[b].cpu().numpy(), ref) < 1e-5, (N, b)
-        assert rel_l2(lm.cpu().numpy(), lm0.cpu().numpy()) < 1e-6
-        rec = hi[:, :T].float() + lo[:, :T].float()
-        tol = 2.0 ** -20 if fmt == "f16" else 2.0 ** -15
-        assert float((rec - lm).abs().max()) <= tol * max(1.0, float(lm.abs().max()))
-        assert float(hi[:, T:].float().abs().max() if rows > T else 0.0) == 0.0          # pad rows untouched
-        # the two kernels' log-magnitudes differ in the last bits, so a hi value may round to the neighbouring 16-bit number
-        assert float((hi.float() - hi0.float()).abs().max()) <= (2.0 ** -10 if fmt == "f16" else 2.0 ** -7) * float(lm.abs().max())
-
-
-@pytest.mark.parametrize("T", [2, 3, 5, 9, 10, 86, 87, 171, 173, 696])
-def test_istft_frame_pair_kernel_matches_oracle_and_scalar_kernel(T):
-    """The inference form of the ISTFT at n_fft 1024 (log-magnitude + raw phase, optional per-clip scale/shift of the
-    phase) on frame pairs: fewer frames than one iteration, odd and even frame counts, frame counts that end exactly on,
-    one past and one short of a CTA's run of 11 * 8 - 3 = 85 hop-blocks, and the BASELINE clip."""
-    from phasegen import ops
-    n_fft, hop, C, B = 1024, 256, 512, 2
-    rng = np.random.default_rng(T)
-    lm = np.abs(rng.standard_normal((B, T, C))).astype(np.float32)
-    ph = (3.0 * rng.standard_normal((B, T, C))).astype(np.float32)
-    ss = np.stack([1.0 + 0.1 * rng.standard_normal((B, C)), 0.2 * rng.standard_normal((B, C))], axis=-1).astype(np.float32)
-    a, b, sst = torch.from_numpy(lm).cuda(), torch.from_numpy(ph).cuda(), torch.from_numpy(ss).cuda()
-    for use_ss in (False, True):
-        run = lambda: ops.istft(a, b, ops.PG_SPEC_POLAR_LOG, n_fft, hop, normalize=False, b_scale_shift=sst if use_ss else None)
-        wv, peak = _with_pair(1, run)
-        wv0, peak0 = _with_pair(0, run)
-        for i in range(B):
-            p = ph[i].astype(np.float64) * ss[i, :, 0] + ss[i, :, 1] if use_ss else ph[i]
-            z = stft_np.polar_to_complex(lm[i].T, np.asarray(p).T)
-            z = np.concatenate([np.zeros((1, T)), z])
-            ref = stft_np.istft(z, hop)
-            assert wv.shape[1] == ref.shape[0] == (T - 1) * hop
-            assert rel_l2(wv[i].cpu().numpy(), ref) < 2e-5, (T, use_ss, i)
-            assert abs(float(peak[i]) - np.max(np.abs(ref))) < 1e-4 * np.max(np.abs(ref))
-        assert rel_l2(wv.cpu().numpy(), wv0.cpu().numpy()) < 2e-6

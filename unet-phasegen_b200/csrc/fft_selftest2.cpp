@@ -10,7 +10,7 @@
 #include <thread>
 #include <vector>
 #define PG_HD inline
-#include "stft_pair.cuh"
+#include "stft_core.cuh"
 using namespace pgfft;
 
 template <int NC> double check_forward() {
@@ -90,104 +90,11 @@ template <int NC> double check_inverse() {
     return sqrt(err / nrm);
 }
 
-// ---- frame-pair programs (stft_pair.cuh): two frames per 32-thread group, packed arithmetic emulated on the host
-double check_forward_pair() {
-    constexpr int NC = 512, TG = 32, NF = 2 * NC;
-    using R = Radix<NC, false>;
-    std::vector<cpx> tw(NF);
-    std::vector<cpx2> tabs(R::TOTAL), s(padded_len2(NC));
-    for (int m = 0; m < NF; ++m) tw[m] = {(float)cos(-2 * M_PI * m / NF), (float)sin(-2 * M_PI * m / NF)};
-    for (int e = 0; e < R::TOTAL; ++e) tabs[e] = pair_table_entry<false>(tw.data(), e);
-    std::vector<double> x[2] = {std::vector<double>(NF), std::vector<double>(NF)};
-    for (auto& xv : x) for (auto& v : xv) v = drand48() - 0.5;
-    std::vector<std::complex<double>> got[2] = {std::vector<std::complex<double>>(NC + 1), std::vector<std::complex<double>>(NC + 1)};
-    std::vector<int> hits(NC + 1, 0);
-    std::barrier bar(TG);
-    auto sync = [&] { bar.arrive_and_wait(); };
-    auto prog = [&](int t) {
-        cpx2 v[16];
-        for (int r = 0; r < 16; ++r) {
-            int m = t + r * TG;
-            v[r] = cpx2_of({(float)(0.5 * x[0][2 * m]), (float)(0.5 * x[0][2 * m + 1])}, {(float)(0.5 * x[1][2 * m]), (float)(0.5 * x[1][2 * m + 1])});
-        }
-        fwd_pair_phase0(s.data(), t, v);
-        sync();
-        fwd_pair_phase1(s.data(), t, tabs.data(), sync);
-        sync();
-        auto emit = [&](int bin, cpx2 X) { cpx a, b; cpx2_split(X, a, b); got[0][bin] = {a.x, a.y}; got[1][bin] = {b.x, b.y}; __atomic_fetch_add(&hits[bin], 1, __ATOMIC_RELAXED); };
-        fwd_pair_fused_last(s.data(), t, tabs.data(), emit);
-    };
-    std::vector<std::thread> th;
-    for (int t = 0; t < TG; ++t) th.emplace_back(prog, t);
-    for (auto& q : th) q.join();
-    double worst = 0;
-    for (int f = 0; f < 2; ++f) {
-        double err = 0, nrm = 0;
-        for (int k = 1; k <= NC; ++k) {
-            if (hits[k] != 1) { printf("pair forward: bin %d emitted %d times\n", k, hits[k]); return 1.0; }
-            std::complex<double> ref = 0;
-            for (int n = 0; n < NF; ++n) ref += x[f][n] * std::polar(1.0, -2 * M_PI * (double)((long)k * n % NF) / NF);
-            err += std::norm(ref - got[f][k]); nrm += std::norm(ref);
-        }
-        worst = fmax(worst, sqrt(err / nrm));
-    }
-    return worst;
-}
-
-double check_inverse_pair() {
-    constexpr int NC = 512, TG = 32, NF = 2 * NC;
-    using R = Radix<NC, true>;
-    std::vector<cpx> tw(NF), win(NC);
-    std::vector<cpx2> tabs(R::TOTAL), s(padded_len2(NC));
-    for (int m = 0; m < NF; ++m) tw[m] = {(float)cos(-2 * M_PI * m / NF), (float)sin(-2 * M_PI * m / NF)};
-    for (int e = 0; e < R::TOTAL; ++e) tabs[e] = pair_table_entry<true>(tw.data(), e);
-    std::vector<double> wn(NF);
-    for (int n = 0; n < NF; ++n) wn[n] = 0.5 - 0.5 * cos(2 * M_PI * n / NF);
-    const float scale = 0.5f / NC;                                  // carried by the window table in the pair form
-    for (int m = 0; m < NC; ++m) win[m] = {(float)wn[2 * m] * scale, (float)wn[2 * m + 1] * scale};
-    std::vector<std::complex<double>> X[2] = {std::vector<std::complex<double>>(NC + 1), std::vector<std::complex<double>>(NC + 1)};
-    for (auto& Xv : X) { for (int k = 1; k <= NC; ++k) Xv[k] = {drand48() - 0.5, drand48() - 0.5}; Xv[0] = 0; }
-    cpx* sa = reinterpret_cast<cpx*>(s.data());                     // the two scalar frame buffers alias the pair buffer
-    cpx* sb = sa + padded_len2(NC);
-    std::barrier bar(TG);
-    auto sync = [&] { bar.arrive_and_wait(); };
-    auto prog = [&](int t) {
-        cpx2 xin[16];
-        for (int j = 0; j < 16; ++j) {
-            const int bin = inv_bin<NC>(t, j);
-            xin[j] = cpx2_of({(float)X[0][bin].real(), (float)X[0][bin].imag()}, {(float)X[1][bin].real(), (float)X[1][bin].imag()});
-        }
-        inv_pair_fused_first(s.data(), t, tabs.data(), xin);
-        sync();
-        inv_pair_passes(s.data(), sa, sb, t, tabs.data(), win.data(), sync);
-    };
-    std::vector<std::thread> th;
-    for (int t = 0; t < TG; ++t) th.emplace_back(prog, t);
-    for (auto& q : th) q.join();
-    double worst = 0;
-    for (int f = 0; f < 2; ++f) {
-        const cpx* sf = f ? sb : sa;
-        double err = 0, nrm = 0;
-        for (int n = 0; n < NF; ++n) {
-            double acc = X[f][NC].real() * ((n & 1) ? -1.0 : 1.0);
-            for (int k = 1; k < NC; ++k) acc += 2.0 * (X[f][k] * std::polar(1.0, 2 * M_PI * (double)((long)k * n % NF) / NF)).real();
-            const double ref = acc / NF * wn[n];
-            const cpx z = sf[pad2(n >> 1)];
-            const double g = (n & 1) ? z.y : z.x;
-            err += (ref - g) * (ref - g); nrm += ref * ref;
-        }
-        worst = fmax(worst, sqrt(err / nrm));
-    }
-    return worst;
-}
-
 int main() {
     double worst = 0, e;
 #define RUN(NC) e = check_forward<NC>(); printf("NC=%d stft frame rel %.3e\n", NC, e); worst = fmax(worst, e); \
                 e = check_inverse<NC>(); printf("NC=%d istft frame rel %.3e\n", NC, e); worst = fmax(worst, e);
     RUN(128) RUN(256) RUN(512) RUN(1024)
-    e = check_forward_pair(); printf("NC=512 stft frame PAIR rel %.3e\n", e); worst = fmax(worst, e);
-    e = check_inverse_pair(); printf("NC=512 istft frame PAIR rel %.3e\n", e); worst = fmax(worst, e);
     if (!(worst < 2e-6)) { printf("FAIL\n"); return 1; }
     printf("OK\n");
     return 0;

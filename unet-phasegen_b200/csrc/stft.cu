@@ -22,11 +22,8 @@
 //          version recomputed 3 per 13).  No atomics on the output; the per-clip peak (utils.py:42) is one
 //          atomicMax per warp on a scalar.
 // hop must be n_fft/4 (true for every configuration of the reference and of BASELINE.json).
-#include <cstdlib>
-
 #include "common.cuh"
 #include "stft_core.cuh"
-#include "stft_pair.cuh"
 
 namespace pg {
 using namespace pgfft;
@@ -184,133 +181,6 @@ stft_kernel(const float* __restrict__ wave, int N, int T, const float2* __restri
     }
 }
 
-
-// ------------------------------------------------------------------------------------ STFT, frame pairs (n_fft 1024)
-// The inference path (log-magnitude fp32 plane + 16-bit hi/lo operand planes) on stft_pair.cuh: a warp owns frames
-// (f, f+1) of one clip and every lane carries the same points of both as packed fp32x2 values, so the transform runs
-// on FADD2/FMUL2/FFMA2 and 128-bit shared-memory accesses.  16 frames per CTA iteration.
-constexpr int kPairWarps = 8;
-constexpr int kPairThreads = 32 * kPairWarps;
-constexpr int kPairPL = padded_len2(512);                   // 16-byte elements of one pair buffer (= two scalar frame buffers)
-constexpr size_t smem_stft_pair() { return sizeof(cpx2) * (Radix<512, false>::TOTAL + (size_t)kPairWarps * kPairPL) + sizeof(cpx) * 512; }
-
-__device__ __forceinline__ f2 fast_log1p_mag2(cpx2 x) {
-    const f2 m2 = fma2(x.x, x.x, x.y * x.y);
-    float a, b;
-    f2_split(m2, a, b);
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(a));
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(b));
-    f2_split(f2_make(a, b) + f2_bcast(1.0f), a, b);
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(a));
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(b));
-    return f2_make(a, b) * f2_bcast(0.693147180559945f);
-}
-
-// 16 windowed points z[t + 32 r] = (x[2m] w[2m], x[2m+1] w[2m+1]) / 2 of one frame, unwindowed (the caller multiplies)
-__device__ __forceinline__ void load_frame_points(const float* __restrict__ w, int N, int frame, bool live, bool aligned, int t, float2* x) {
-    const int p0 = frame * 256 - 512;                       // padded sample p <-> wave index p - n_fft/2 (librosa center=True)
-    if (live && aligned && p0 >= 0 && p0 + 1024 <= N) {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) x[r] = __ldg(reinterpret_cast<const float2*>(w + p0) + t + 32 * r);
-    } else if (live) {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            int n0 = p0 + 2 * (t + 32 * r), n1 = n0 + 1;    // reflected at both ends
-            if (n0 < 0) n0 = -n0;
-            if (n0 >= N) n0 = 2 * (N - 1) - n0;
-            if (n1 < 0) n1 = -n1;
-            if (n1 >= N) n1 = 2 * (N - 1) - n1;
-            x[r].x = (n0 >= 0 && n0 < N) ? __ldg(w + n0) : 0.f;
-            x[r].y = (n1 >= 0 && n1 < N) ? __ldg(w + n1) : 0.f;
-        }
-    } else {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) x[r] = make_float2(0.f, 0.f);
-    }
-}
-
-template <int FAST>                                          // 1: bf16 operand planes, 2: fp16
-__global__ void __launch_bounds__(kPairThreads, 2)
-stft_pair_kernel(const float* __restrict__ wave, int N, int T, const float2* __restrict__ tw_g, float* __restrict__ out_a,
-                 uint16_t* __restrict__ op_hi, uint16_t* __restrict__ op_lo, long long op_batch_stride, int frames_per_cta) {
-    using R = Radix<512, false>;
-    extern __shared__ __align__(16) unsigned char smem_pair[];
-    cpx2* tabs = reinterpret_cast<cpx2*>(smem_pair);         // broadcast twiddle tables
-    cpx2* bufs = tabs + R::TOTAL;                            // one pair buffer per warp
-    cpx* win = reinterpret_cast<cpx*>(bufs + (size_t)kPairWarps * kPairPL);   // (w[2m], w[2m+1]) / 2, periodic Hann
-
-    const int tid = threadIdx.x;
-    const cpx* twc = reinterpret_cast<const cpx*>(tw_g);
-    for (int e = tid; e < R::TOTAL; e += kPairThreads) tabs[e] = pair_table_entry<false>(twc, e);
-    for (int m = tid; m < 512; m += kPairThreads) win[m] = {0.25f - 0.25f * tw_g[2 * m].x, 0.25f - 0.25f * tw_g[2 * m + 1].x};
-    __syncthreads();
-
-    const int b = blockIdx.y;
-    const int warp = tid >> 5, t = tid & 31;
-    cpx2* s = bufs + (size_t)warp * kPairPL;
-    auto sync = [] { __syncwarp(); };
-    const float* w = wave + (size_t)b * N;
-    const bool aligned = (N & 1) == 0 && (reinterpret_cast<uintptr_t>(wave) & 7) == 0;
-    const int f_begin = blockIdx.x * frames_per_cta;
-
-    for (int f0 = f_begin; f0 < f_begin + frames_per_cta && f0 < T; f0 += 2 * kPairWarps) {
-        const int fa = f0 + 2 * warp, fb = fa + 1;
-        const bool live_a = fa < T, live_b = fb < T;
-        cpx2 v[16];
-        {
-            float2 xa[16], xb[16];
-            load_frame_points(w, N, fa, live_a, aligned, t, xa);
-            load_frame_points(w, N, fb, live_b, aligned, t, xb);
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const cpx wv = win[t + 32 * r];
-                v[r] = {f2_make(xa[r].x * wv.x, xb[r].x * wv.x), f2_make(xa[r].y * wv.y, xb[r].y * wv.y)};
-            }
-        }
-        fwd_pair_phase0(s, t, v);
-        sync();
-        fwd_pair_phase1(s, t, tabs, sync);
-        sync();
-
-        const size_t row = ((size_t)b * T + fa) * 512;                    // frame B: + 512
-        const size_t orow = (size_t)b * op_batch_stride + (size_t)fa * 512;
-        auto emit = [&](int bin, cpx2 x) {
-            const f2 a2 = fast_log1p_mag2(x);
-            float aa, ab;
-            f2_split(a2, aa, ab);
-            uint32_t hi2, lo2;                                            // low half: frame A, high half: frame B
-            if (FAST == 2) {
-                const __half2 h = __floats2half2_rn(aa, ab);
-                const float2 hf = __half22float2(h);
-                float la, lb;
-                f2_split(a2 - f2_make(hf.x, hf.y), la, lb);
-                const __half2 l = __floats2half2_rn(la, lb);
-                hi2 = *reinterpret_cast<const uint32_t*>(&h); lo2 = *reinterpret_cast<const uint32_t*>(&l);
-            } else {
-                const __nv_bfloat162 h = __floats2bfloat162_rn(aa, ab);
-                const float2 hf = __bfloat1622float2(h);
-                float la, lb;
-                f2_split(a2 - f2_make(hf.x, hf.y), la, lb);
-                const __nv_bfloat162 l = __floats2bfloat162_rn(la, lb);
-                hi2 = *reinterpret_cast<const uint32_t*>(&h); lo2 = *reinterpret_cast<const uint32_t*>(&l);
-            }
-            const size_t o = row + bin - 1, oo = orow + bin - 1;
-            if (live_a) {
-                out_a[o] = aa;
-                op_hi[oo] = (uint16_t)hi2;
-                op_lo[oo] = (uint16_t)lo2;
-            }
-            if (live_b) {
-                out_a[o + 512] = ab;
-                op_hi[oo + 512] = (uint16_t)(hi2 >> 16);
-                op_lo[oo + 512] = (uint16_t)(lo2 >> 16);
-            }
-        };
-        fwd_pair_fused_last(s, t, tabs, emit);
-        sync();                                                           // the buffer is rewritten by the next pair
-    }
-}
-
 // ----------------------------------------------------------------------------------- ISTFT
 __device__ __forceinline__ cpx spec_value(float a, float p, int mode) {
     if (mode == PG_SPEC_CARTESIAN) return {a, p};
@@ -446,142 +316,6 @@ istft_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int
     if (nonfinite && bad) atomicOr(nonfinite + b, 1);
 }
 
-// ------------------------------------------------------------------------------------ ISTFT, frame pairs (n_fft 1024)
-// The inference path (log-magnitude + phase planes, optional per-(clip, bin) scale/shift of the phase) on stft_pair.cuh.
-// A CTA of 4 warps walks a run of frames, 8 per iteration (one frame PAIR per warp); a pair is transformed in two
-// adjacent slots of the ring of windowed frames (used as ONE 16-byte-element buffer during the passes) and the last pass
-// writes the two windowed frames back to their own slots, where the overlap-add gathers them exactly like the
-// one-frame-per-warp kernel does.
-constexpr int kIPairWarps = 4;
-constexpr int kIPairThreads = 32 * kIPairWarps;
-constexpr int kIPairFC = 2 * kIPairWarps;                   // frames per iteration
-constexpr int kIPairRing = kIPairFC + 4;                    // even: a pair never wraps around the ring
-constexpr size_t smem_istft_pair() {
-    return sizeof(float) * 256 + sizeof(cpx2) * Radix<512, true>::TOTAL + sizeof(cpx) * (512 + (size_t)kIPairRing * kPairPL) + sizeof(float2) * 512;
-}
-
-__global__ void __launch_bounds__(kIPairThreads, 3)
-istft_pair_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, int T, const float2* __restrict__ tw_g,
-                  float* __restrict__ wave, unsigned* __restrict__ peak_bits, int* __restrict__ nonfinite, int blocks_per_cta,
-                  const float2* __restrict__ b_ss, int b_ss_stride) {
-    using R = Radix<512, true>;
-    constexpr int NC = 512, HOP = 256, FC = kIPairFC, RING = kIPairRing, PL = kPairPL;
-    extern __shared__ __align__(16) unsigned char smem_pair[];
-    cpx2* tabs = reinterpret_cast<cpx2*>(smem_pair);
-    cpx* ring = reinterpret_cast<cpx*>(tabs + R::TOTAL);    // RING scalar frame buffers; slots (2p, 2p+1) double as a pair buffer
-    cpx* win = ring + (size_t)RING * PL;                    // synthesis Hann (w[2m], w[2m+1]) times the 1/(2 NC) of the inverse transform
-    float2* ss_tab = reinterpret_cast<float2*>(win + NC);   // [NC] scale/shift of the second plane, only when b_ss
-    float* wss_full = reinterpret_cast<float*>(ss_tab + NC);   // [HOP] 1 / sum of w^2 over the 4 covering frames
-
-    const int tid = threadIdx.x;
-    const cpx* twc = reinterpret_cast<const cpx*>(tw_g);
-    const float scale = 0.5f / NC, inv_scale = 2.0f * NC;   // powers of two: folding the scale into the window is exact
-    for (int e = tid; e < R::TOTAL; e += kIPairThreads) tabs[e] = pair_table_entry<true>(twc, e);
-    for (int m = tid; m < NC; m += kIPairThreads) win[m] = {(0.5f - 0.5f * tw_g[2 * m].x) * scale, (0.5f - 0.5f * tw_g[2 * m + 1].x) * scale};
-    for (int i = tid; i < HOP; i += kIPairThreads) {
-        float acc = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const float wn = 0.5f - 0.5f * tw_g[q * HOP + i].x; acc += wn * wn; }
-        wss_full[i] = acc > 1.17549435e-38f ? 1.0f / acc : 1.0f;
-    }
-    const int b = blockIdx.y;
-    if (b_ss) for (int m = tid; m < NC; m += kIPairThreads) ss_tab[m] = __ldg(b_ss + (size_t)b * b_ss_stride + m);
-    __syncthreads();
-
-    const int J0 = blockIdx.x * blocks_per_cta;             // output hop-blocks [J0, J1) of this CTA
-    const int J1 = min(J0 + blocks_per_cta, T - 1);
-    const int F0 = J0 - 1;                                  // first frame needed
-    const int n_iter = (J1 - J0 + 3 + FC - 1) / FC;
-    const int warp = tid >> 5, t = tid & 31;
-    auto sync = [] { __syncwarp(); };
-    float* wv = wave + (size_t)b * (size_t)(T - 1) * HOP;
-    float pk = 0.f;
-    bool bad = false;
-
-    // the 16 (a, b) input pairs of both frames are fetched one iteration ahead of their use
-    float ra[2][16], rb[2][16];
-    auto is_live = [&](int frame) { return frame >= 0 && frame < T && frame <= J1 + 1; };
-    auto fetch = [&](int frame, float* a, float* bq) {
-        if (!is_live(frame)) return;
-        const size_t row = ((size_t)b * T + frame) * NC;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const size_t idx = row + inv_bin<NC>(t, j) - 1;
-            a[j] = __ldg(in_a + idx);
-            bq[j] = __ldg(in_b + idx);
-        }
-    };
-    fetch(F0 + 2 * warp, ra[0], rb[0]);
-    fetch(F0 + 2 * warp + 1, ra[1], rb[1]);
-
-    for (int it = 0; it < n_iter; ++it) {
-        const int F = F0 + it * FC;
-        const int fa = F + 2 * warp;
-        const bool live = is_live(fa) || is_live(fa + 1);   // a dead frame of a live pair transforms stale values that are never read
-        cpx* sa = ring + (size_t)((fa - F0) % RING) * PL;   // (fa - F0) is even and RING is even: slot + 1 is frame B's
-        cpx* sb = sa + PL;
-        cpx2* s = reinterpret_cast<cpx2*>(sa);
-        if (live) {
-            cpx2 x[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float pa = rb[0][j], pb = rb[1][j];
-                if (b_ss) { const float2 ss = ss_tab[inv_bin<NC>(t, j) - 1]; pa = fmaf(pa, ss.x, ss.y); pb = fmaf(pb, ss.x, ss.y); }
-                // expm1(a) e^{j p} (demo.py:39), special functions as in spec_value
-                const f2 mag = f2_make(__expf(ra[0][j]), __expf(ra[1][j])) - f2_bcast(1.0f);
-                x[j] = {mag * f2_make(__cosf(pa), __cosf(pb)), mag * f2_make(__sinf(pa), __sinf(pb))};
-            }
-            inv_pair_fused_first(s, t, tabs, x);
-        }
-        if (it + 1 < n_iter) { fetch(fa + FC, ra[0], rb[0]); fetch(fa + FC + 1, ra[1], rb[1]); }
-        sync();
-        inv_pair_passes(s, sa, sb, t, tabs, win, sync);
-        __syncthreads();
-
-        // output hop-block jb (trimmed coordinates) is covered by frames jb-1 .. jb+2; within frame jb-1+q its samples sit
-        // at offset (3-q)*hop + i
-        const int lo = max(J0, F - 2), hi = min(J1, F + FC - 2);
-        for (int u = tid; u < (hi - lo) * (HOP / 4); u += kIPairThreads) {
-            const int jb = lo + u / (HOP / 4), i = (u % (HOP / 4)) * 4;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), wss;
-            const bool interior = jb >= 1 && jb + 2 < T;
-            if (interior) wss = *reinterpret_cast<const float4*>(wss_full + i);
-            else wss = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int fr = jb - 1 + q;
-                if (fr < 0 || fr >= T) continue;
-                const cpx* fbuf = ring + (size_t)((fr - F0) % RING) * PL;
-                const int m = ((3 - q) * HOP + i) >> 1;
-                const cpx z0 = fbuf[pad2(m)], z1 = fbuf[pad2(m + 1)];
-                acc.x += z0.x; acc.y += z0.y; acc.z += z1.x; acc.w += z1.y;
-                if (!interior) {
-                    const cpx w0 = win[m], w1 = win[m + 1];
-                    const float a0 = w0.x * inv_scale, a1 = w0.y * inv_scale, a2 = w1.x * inv_scale, a3 = w1.y * inv_scale;
-                    wss.x += a0 * a0; wss.y += a1 * a1; wss.z += a2 * a2; wss.w += a3 * a3;
-                }
-            }
-            if (!interior) {                                // edge blocks (two per clip): divide where > tiny (librosa)
-                wss.x = wss.x > 1.17549435e-38f ? 1.0f / wss.x : 1.0f; wss.y = wss.y > 1.17549435e-38f ? 1.0f / wss.y : 1.0f;
-                wss.z = wss.z > 1.17549435e-38f ? 1.0f / wss.z : 1.0f; wss.w = wss.w > 1.17549435e-38f ? 1.0f / wss.w : 1.0f;
-            }
-            float4 y;
-            y.x = acc.x * wss.x; y.y = acc.y * wss.y; y.z = acc.z * wss.z; y.w = acc.w * wss.w;
-            *reinterpret_cast<float4*>(wv + (size_t)jb * HOP + i) = y;
-            const float mx = fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w)));
-            if (!(mx <= 3.402823466e+38f) || y.x != y.x || y.y != y.y || y.z != y.z || y.w != y.w) bad = true;
-            pk = fmaxf(pk, mx);
-        }
-        __syncthreads();                                    // the next iteration overwrites the oldest FC frames
-    }
-    if (peak_bits) {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
-        if ((tid & 31) == 0 && pk > 0.f) atomicMax(peak_bits + b, __float_as_uint(pk));
-    }
-    if (nonfinite && bad) atomicOr(nonfinite + b, 1);
-}
-
 __global__ void peak_normalize_kernel(float* __restrict__ wave, const unsigned* __restrict__ peak_bits, int n) {
     const int b = blockIdx.y;
     float pk = __uint_as_float(peak_bits[b]);
@@ -636,33 +370,12 @@ stitch_kernel(const float* __restrict__ windows, int n_windows, int win, int ste
     }
 }
 
-// A/B hook: PG_STFT_PAIR=0 keeps the one-frame-per-warp kernels for n_fft 1024 as well
-static bool pair_kernels_enabled() {
-    const char* e = getenv("PG_STFT_PAIR");                  // read per call: the tests run both forms in one process
-    return !(e && atoi(e) == 0);
-}
-
 template <int NC>
 static int launch_stft(const float* wave, int B, int N, int T, const float* tw, int mode, float* a, float* bq,
                        uint16_t* hi, uint16_t* lo, long long bs, int fmt, cudaStream_t st, const float* proj_mag = nullptr,
                        float std_mean = 0.f, float std_inv = 1.f) {
     using Cfg = FrameCfg<NC>;
     const bool fast = mode == PG_STFT_LOGMAG && a && !bq && hi && lo;
-    if (NC == 512 && fast && pair_kernels_enabled()) {       // n_fft 1024 inference path: frame pairs on packed fp32x2 arithmetic
-        auto kp = fmt == PG_FMT_F16 ? stft_pair_kernel<2> : stft_pair_kernel<1>;
-        const size_t smp = smem_stft_pair();
-        static bool configured_pair[kMaxDevices] = {};
-        bool& cfgp = configured_pair[current_device_slot()];
-        if (!cfgp) {
-            cudaFuncSetAttribute(stft_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
-            cudaFuncSetAttribute(stft_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
-            cfgp = true;
-        }
-        const int fpc = 8 * kPairWarps;                      // 4 iterations of 16 frames: tables built once per 64 frames
-        dim3 gridp((T + fpc - 1) / fpc, B);
-        kp<<<gridp, kPairThreads, smp, st>>>(wave, N, T, reinterpret_cast<const float2*>(tw), a, hi, lo, bs, fpc);
-        return check_launch("stft_pair_kernel");
-    }
     auto k = !fast ? stft_kernel<NC, 0> : fmt == PG_FMT_F16 ? stft_kernel<NC, 2> : stft_kernel<NC, 1>;
     const size_t sm = Cfg::smem_stft();
     static bool configured_dev[kMaxDevices] = {};
@@ -683,18 +396,6 @@ template <int NC>
 static int launch_istft(const float* a, const float* bq, int mode, int B, int T, const float* tw, float* wave,
                         float* peak, int* nonfinite, cudaStream_t st, const float* b_ss, int b_ss_stride) {
     using Cfg = FrameCfg<NC>;
-    if (NC == 512 && mode == PG_SPEC_POLAR_LOG && bq && pair_kernels_enabled()) {   // n_fft 1024 inference path: frame pairs
-        const size_t smp = smem_istft_pair();
-        static bool configured_pair[kMaxDevices] = {};
-        bool& cfgp = configured_pair[current_device_slot()];
-        if (!cfgp) { cudaFuncSetAttribute(istft_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp); cfgp = true; }
-        const int bpc = 11 * kIPairFC - 3;                   // 11 iterations per run, 3 halo frames recomputed per run
-        dim3 gridp((T - 1 + bpc - 1) / bpc, B);
-        istft_pair_kernel<<<gridp, kIPairThreads, smp, st>>>(a, bq, T, reinterpret_cast<const float2*>(tw), wave,
-                                                             reinterpret_cast<unsigned*>(peak), nonfinite, bpc,
-                                                             reinterpret_cast<const float2*>(b_ss), b_ss_stride);
-        return check_launch("istft_pair_kernel");
-    }
     auto k = (mode == PG_SPEC_POLAR_LOG && bq) ? istft_kernel<NC, true> : istft_kernel<NC, false>;
     const size_t sm = Cfg::smem_istft();
     static bool configured_dev[kMaxDevices] = {};

@@ -9,8 +9,6 @@
 //   * pg_wgrad_simt     exact-fp32 weight gradient (small channel counts, GPU-side check of wgrad_tc)
 //   * pg_unpack_grad    packed [k][C_out][C_in] gradient -> torch Conv / ConvT weight layout
 //   * pg_adam_step      torch.optim.Adam defaults (train.py:26-27), fused, fp32 state
-#include <cstdlib>
-
 #include "common.cuh"
 #include "conv_plan.h"
 
@@ -228,8 +226,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
                         reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
                       ((reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo)) & 7) == 0 ? n / 4 : 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        // streaming (evict-first) accesses: 28 B/parameter pass through once; they should not push the tensor-core kernels'
-        // weight slabs and activations out of L2 when the update runs beside them (one-GPU overlap, phasegen/train.py)
+        // streaming (evict-first) accesses: 28 B/parameter pass through exactly once per step
         float4 pi = __ldcs(reinterpret_cast<const float4*>(p) + i);
         float4 gi;
         if (g_bf16) {
@@ -342,7 +339,6 @@ extern "C" int pg_adam_step(float* p, const void* g, int g_dtype, float* m, floa
     const float bc1 = 1.f - powf(beta1, (float)step);
     const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
     int gx = (int)((n / 4 + 255) / 256); if (gx > 148 * 16) gx = 148 * 16; if (gx < 1) gx = 1;
-    if (const char* e = getenv("PG_ADAM_MAX_CTAS")) { const int cap = atoi(e); if (cap > 0 && gx > cap) gx = cap; }   // experiment hook
     adam_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, static_cast<const float*>(g), m, v, (size_t)n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale, w_hi, w_lo, g_dtype == PG_DT_BF16 ? 1 : 0);
     return check_launch("adam_kernel");
 }

@@ -45,7 +45,6 @@ class TrainExecutor(UNetExecutor):
                      for d, has in ((self.dn_desc[i], lv.down_norm), (self.up_desc[i], lv.up_norm)) if has)
         self.dgb_flat = torch.zeros(max(n_norm, 1), **f32)
         self.grad_hook = None                                           # called with each weight gradient once it is complete
-        self.layer_hook = None                                          # called once a layer's wgrad AND dgrad are queued
         off = 0
         for i, lv in enumerate(levels):
             for which, desc, has_norm in (("dn", self.dn_desc[i], lv.down_norm), ("up", self.up_desc[i], lv.up_norm)):
@@ -128,8 +127,6 @@ class TrainExecutor(UNetExecutor):
                 ops.conv_simt(mirror, dz.hi, w_t[2], din)
             else:
                 ops.conv_tc(mirror, dz.hi, dz.lo, w_t[0], w_t[1], din, None)
-        if self.layer_hook is not None:
-            self.layer_hook(dw)                 # this layer's weight planes have been read for the last time in this step
 
     def backward(self, dn_norm, up_norm, d_out=None):
         """Consumes the buffers of the last run(); d_out [B][T][2C] fp32 channels-last (default: the
@@ -213,9 +210,6 @@ class TrainStep:
                 self.ex.reserve_sms_in_backward(n_res)
         self.t = 0
         self._works = []
-        self._side = None
-        self._early = set()
-        self.overlap_update = os.environ.get("PG_ADAM_OVERLAP", "0") == "1"
         ex = self.ex
         tc = ex.prec != PG_PREC_FP32_SIMT
         # (parameter storage, gradient buffer, bf16 planes to refresh) in packed order
@@ -315,42 +309,18 @@ class TrainStep:
                 else:
                     works.append((g, dist.all_reduce(g, async_op=True)))
             ex.grad_hook = hook
-        self._early = set()
-        if self.world == 1 and self.overlap_update and ex.prec != PG_PREC_FP32_SIMT:
-            # one GPU: each layer's Adam is queued on a side stream as soon as that layer's data gradient (the last reader of
-            # its weight planes in this step) is queued, so the HBM-bound update streams underneath the tensor-bound
-            # kernels of the layers backward reaches later
-            cur = torch.cuda.current_stream()
-            if self._side is None:
-                self._side = torch.cuda.Stream()
-            side = self._side
-            by_grad = {it["g"].data_ptr(): it for it in self.items if it["conv"] is not None}
-
-            def layer_hook(g):
-                it = by_grad.get(g.data_ptr())
-                if it is None:
-                    return
-                ev = torch.cuda.Event()
-                ev.record(cur)
-                side.wait_event(ev)
-                with torch.cuda.stream(side):
-                    self._adam(it, 1.0, step=self.t + 1)
-                self._early.add(id(it))
-            ex.layer_hook = layer_hook
         ex.backward(dn, up)
         ex.grad_hook = None
-        ex.layer_hook = None
         self._works = works
         return loss3
 
-    def _adam(self, it, scale, step=None):
+    def _adam(self, it, scale):
         ex = self.ex
         hi = lo = None
         if it["conv"] is not None:            # refresh the tensor-core operand planes in the same pass
             which, i = it["conv"]
             hi, lo = (ex.wd[i] if which == "dn" else ex.wu[i])[:2]
-        ops.adam_step(it["p"], it["g"], it["m"], it["v"], self.lr, self.betas[0], self.betas[1], self.eps,
-                      self.t if step is None else step, scale, hi, lo)
+        ops.adam_step(it["p"], it["g"], it["m"], it["v"], self.lr, self.betas[0], self.betas[1], self.eps, self.t, scale, hi, lo)
 
     def apply(self):
         """Adam (train.py:62) on the gradients of the last forward_backward(), refreshing the operand planes."""
@@ -378,13 +348,10 @@ class TrainStep:
                 if id(it) not in done:
                     adam(it)
         else:
-            early = getattr(self, "_early", ())
-            if early:
-                torch.cuda.current_stream().wait_stream(self._side)
+            # (Tried: each layer's Adam on a side stream underneath the remaining backward kernels.  No gain -- 8.87 vs 9.00 ms:
+            #  the persistent tensor-core kernels fill every SM's shared memory, so the update only ran in the gaps.)
             for it in self.items:
-                if id(it) not in early:
-                    adam(it)
-            self._early = set()
+                adam(it)
         if ex.prec == PG_PREC_FP32_SIMT:          # SIMT operand layouts are re-packed from the updated weights
             blocks = net._blocks()
             ws = [b._parts["down"].weight for b in blocks] + [b._parts["up"].weight for b in blocks]
