@@ -119,6 +119,9 @@ class Dist:
             raise SystemExit("bench.py: no CUDA device; the phasegen path has no CPU fallback")
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
+        # run (and first-touch the pinned staging buffers) on the NUMA node of this rank's GPU; best effort
+        from phasegen import hostmem
+        self.host_binding = hostmem.bind_to_gpu_node(self.local) if os.environ.get("PG_NO_NUMA_BIND") != "1" else {"numa_node": None, "disabled": True}
         if self.world > 1:
             import torch.distributed as dist
             dist.init_process_group("nccl", device_id=self.dev)
@@ -131,14 +134,17 @@ class Dist:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(self, fn, steps):
-        """Total milliseconds of `steps` calls, max over ranks."""
+    def timed(self, fn, steps, finish=None):
+        """Total milliseconds of `steps` calls, max over ranks.  `finish` (optional) runs after the last call and before
+        the closing event: it orders work the calls left on other streams onto the timed stream."""
         import torch
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()
         e1.record()
         self.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
@@ -534,11 +540,31 @@ def main():
     def step_resident():
         return pipe(wave)
 
-    def step_e2e():
-        # the public host-buffer call: pinned host wave in, pinned host wave out, copies inside
+    def step_e2e_sync():
+        # the public host-buffer call, one batch at a time: pinned host wave in, pinned host wave out, copies inside;
+        # the call returns with its downloads ordered on the current stream
         pipe.run_host(host_in, host_out, chunks=e2e_chunks)
 
+    # ... and as a stream of batches (the serving form, `pipelined=True`): the same copies every step, but the first
+    # upload of step i+1 and the last download of step i run underneath the neighbouring step's GPU work; the result of
+    # a step is awaited (event) two steps later, into alternating pinned output buffers
+    host_outs = [host_out, torch.empty(B, N, dtype=torch.float32).pin_memory()]
+    pend, e2e_i = [None, None], [0]
+
+    def step_e2e():
+        k = e2e_i[0] & 1
+        if pend[k] is not None:
+            pend[k].synchronize()                              # a consumer would read host_outs[k] here
+        pend[k] = pipe.run_host(host_in, host_outs[k], chunks=stream_chunks, pipelined=True)
+        e2e_i[0] += 1
+
+    def finish_e2e():
+        for ev in pend:                                        # every download of the timed steps lands inside the timed region
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+
     e2e_chunks = pipe.suggest_chunks(B, N, dev) if args.e2e_chunks == 0 else args.e2e_chunks
+    stream_chunks = 1 if args.e2e_chunks == 0 else args.e2e_chunks      # stream of batches: copies hide behind the neighbouring batches
     sampler = ClockSampler(D.local)
     if rank == 0:
         sampler.start()                                        # nvidia-smi needs ~0.1 s to deliver its first sample: start it
@@ -549,8 +575,13 @@ def main():
     launches = _lib.launches - l0
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
+        step_e2e_sync()
+    ms_e2e_sync = D.timed(step_e2e_sync, args.steps)
+    for _ in range(2):
         step_e2e()
-    ms_e2e = D.timed(step_e2e, args.steps)
+    ms_e2e = D.timed(step_e2e, args.steps, finish=finish_e2e)
+    torch.cuda.synchronize()
+    e2e_identical = bool(torch.equal(host_outs[0], host_outs[1]))   # same input every step: both buffers hold the same waves
 
     audio_s = world * B * clip_s
     value = audio_s / (ms / args.steps / 1e3)
@@ -659,28 +690,40 @@ def main():
 
     single = longf = lib = train = None
     if not args.no_extras:
-        del pipe
-        net.__dict__["_exec"].clear(); net.__dict__["_packed"].clear()
-        torch.cuda.empty_cache()
-        if world == 1:
-            single = single_clip_leg(args, D, net)
+        # the side legs must never cost the headline line: a leg that fails is reported as {"error": ...}
+        def guarded(name, fn):
+            try:
+                return fn()
+            except Exception as e:                               # noqa: BLE001 -- reported, not swallowed
+                print(f"bench.py: leg '{name}' failed: {type(e).__name__}: {e}", file=sys.stderr, flush=True)
+                return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+        def reset():
             net.__dict__["_exec"].clear(); net.__dict__["_packed"].clear()
             torch.cuda.empty_cache()
-        longf = longform_leg(args, D, net)
-        net.__dict__["_exec"].clear(); net.__dict__["_packed"].clear()
-        torch.cuda.empty_cache()
+        del pipe
+        reset()
+        if world == 1:
+            single = guarded("single_clip", lambda: single_clip_leg(args, D, net))
+            reset()
+        longf = guarded("longform", lambda: longform_leg(args, D, net))
+        reset()
         if world == 1 and rank == 0:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import torch_baseline
-            lib = torch_baseline.inference_baseline(wave, N_FFT, HOP, clip_s, steps=3, warmup=2)
+            lib = guarded("gpu_library_baseline", lambda: torch_baseline.inference_baseline(wave, N_FFT, HOP, clip_s, steps=3, warmup=2))
             torch.cuda.empty_cache()
         del net
         torch.cuda.empty_cache()
-        t = train_leg(args, D, with_library_baseline=True)
-        train = {k: t[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "dtype", "config", "e2e", "gpu_launches",
-                                   "roofline", "loss_trace") if k in t}
-        if "gpu_library_baseline" in t:
-            train["gpu_library_baseline"] = t["gpu_library_baseline"]
+
+        def train_side():
+            t = train_leg(args, D, with_library_baseline=True)
+            out = {k: t[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "dtype", "config", "e2e", "gpu_launches",
+                                     "roofline", "loss_trace") if k in t}
+            if "gpu_library_baseline" in t:
+                out["gpu_library_baseline"] = t["gpu_library_baseline"]
+            return out
+        train = guarded("train", train_side)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:     # reported at N = 1 only
@@ -699,7 +742,15 @@ def main():
                            "l2_policy": f"inputs larger than L2 ({B * N * 4 / 1e6:.0f} MB wave, >2 GB of activations per step)",
                            "timing": "CUDA events on the launch stream, max over ranks"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * N * 4, "d2h_bytes_per_step": B * N * 4,
-                        "ms_per_step": ms_e2e / args.steps, "sub_batches": e2e_chunks},
+                        "ms_per_step": ms_e2e / args.steps, "sub_batches": stream_chunks,
+                        "form": "stream of batches (run_host(pipelined=True)): every step copies its clips in from pinned host memory and its waves "
+                                "back out; the copies of a step run underneath the GPU work of the neighbouring steps (two sets of staging buffers); "
+                                "results awaited by event, alternating pinned output buffers",
+                        "one_batch_at_a_time": {"value": audio_s / (ms_e2e_sync / args.steps / 1e3), "ms_per_step": ms_e2e_sync / args.steps,
+                                                "sub_batches": e2e_chunks,
+                                                "form": "run_host(): the call returns with its downloads ordered on the current stream; "
+                                                        "wave-aligned sub-batches ramp 1-2-4-..-4-2-1 waves so copies hide inside the call"},
+                        "outputs_identical_across_steps": e2e_identical, "host_binding": D.host_binding},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
                 "all_three_product_form": alt, "other_mixed_form": alt1,
                 "gpu_library_baseline": lib, "train": train, "single_clip": single, "longform": longf}

@@ -148,6 +148,25 @@ def test_host_buffer_call_equals_device_call():
     with pytest.raises(RuntimeError, match="add up"):
         pipe.run_host(h_in, h_out2, chunks=[3, 3])
     assert sum(pipe.suggest_chunks(B, h_in.shape[1], "cuda")) == B
+    # stream of batches (pipelined=True): calls are not ordered against the current stream, each returns the event of its last
+    # download; different inputs per call and alternating output buffers, six calls back to back
+    ins = [synth.synthetic_waves(B, (T - 1) * hop, sr=16000, seed=20 + i).pin_memory() for i in range(3)]
+    outs = [torch.empty_like(h_in).pin_memory() for _ in range(2)]
+    want = [torch.cat([pipe(x[a:b].cuda()).cpu() for a, b in ((0, 3), (3, 6), (6, 7))]) for x in ins]
+    torch.cuda.synchronize()
+    pend, got = [None, None], []
+    for i in range(6):
+        k = i & 1
+        if pend[k] is not None:
+            pend[k][0].synchronize()
+            got.append((pend[k][1], outs[k].clone()))
+        pend[k] = (pipe.run_host(ins[i % 3], outs[k], chunks=[3, 3, 1], pipelined=True), i % 3)
+    for k in ((6 & 1), (7 & 1)):
+        pend[k][0].synchronize()
+        got.append((pend[k][1], outs[k].clone()))
+    assert len(got) == 6
+    for j, y in got:
+        assert torch.equal(y, want[j])
 
 
 def test_online_training_pairs_match_the_offline_stage():

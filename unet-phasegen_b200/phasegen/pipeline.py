@@ -130,10 +130,13 @@ class PhaseGenPipeline:
         return _GraphedPipeline(graph, static_in, static_out)
 
     def suggest_chunks(self, B, n_samples, device, max_waves=6):
-        """Sub-batch sizes for run_host: a one-wave head and tail (the only copies that are exposed are the first
-        upload and the last download, so they should be small) and middle sub-batches whose tile count in the
-        heaviest convolution fills whole waves of the persistent grid (a sub-batch that spills a few tiles
-        into an extra wave pays for the whole wave).  From the tiling plan of the outermost up convolution."""
+        """Sub-batch sizes for run_host.  Every size fills whole waves of the persistent grid in the heaviest convolution
+        (a sub-batch that spills a few tiles into an extra wave pays for the whole wave), and the sizes RAMP: 1, 2, 4
+        waves at the head, `max_waves` in the middle, 4, 2, 1 at the tail.  The upload of sub-batch j+1 has to land while
+        sub-batch j computes, and the download of sub-batch j-1 has to drain while j computes: with a one-wave head
+        followed directly by a six-wave sub-batch the second upload needed ~49 GB/s of PCIe to keep the GPU busy
+        (78 MB during 1.6 ms); the ramp needs a third of that, and the exposed first upload / last download stay one wave
+        long.  From the tiling plan of the outermost up convolution."""
         import ctypes
         from . import _lib
         T = self.frames(n_samples)
@@ -147,23 +150,27 @@ class PhaseGenPipeline:
         n_ntiles, nb, pair, n_cotiles, OS = out[1], out[2], out[4], out[9], out[10]
         slabs = (n_cotiles // 2 if pair else n_cotiles) * OS * n_ntiles
         units = 74 if pair else 148
-        cap = lambda waves: max(nb, nb * ((waves * units) // slabs))      # clips whose tiles fill at most `waves` waves
-        edge, mid = cap(1), cap(max_waves)
-        if B <= 2 * edge + nb:
-            return [B]
-        sizes, rest = [edge], B - 2 * edge
-        while rest > 0:
-            sizes.append(min(mid, rest))
-            rest -= sizes[-1]
-        return sizes + [edge]
+        return ramp_sizes(B, lambda waves: max(nb, nb * ((waves * units) // slabs)), nb, max_waves)
 
-    def run_host(self, host_in, host_out, chunks=4):
+    def run_host(self, host_in, host_out, chunks=4, pipelined=False):
         """End-to-end call on HOST buffers (pinned float32 [B, N] in and out): the batch is cut into
         sub-batches (`chunks`: how many equal ones, or an explicit list of sizes, e.g. from suggest_chunks)
-        whose host->device copy, GPU work and device->host copy overlap on three streams through two
-        persistent device staging slots (no allocation inside the loop), so only the first upload and the
-        last download are exposed.  Returns when every download has been ordered on the current stream
-        (synchronise it before reading host_out)."""
+        whose host->device copy, GPU work and device->host copy overlap on three streams.  Every sub-batch has its
+        own persistent device staging buffers (in and out: 2 x 4 B per sample of the batch in total, allocated once per
+        batch geometry), so the upload stream never waits for a free slot: it runs ahead of the GPU work by as much as
+        the PCIe rate allows.  Returns when every download has been ordered on the current stream (synchronise it
+        before reading host_out).
+
+        pipelined=True is the serving form for a stream of batches: the call does not order its copies against the
+        current stream at entry or exit and alternates between two sets of staging buffers, so the uploads of batch i+1
+        run underneath the GPU work of batch i and the downloads of batch i underneath batch i+1 (each staging buffer
+        is guarded by its own events: an upload waits until the batch two calls back has been read from it, a sub-batch
+        waits until its previous output has drained).  Throughput is then max(copies, GPU work) for any `chunks`,
+        including a single sub-batch (`chunks=1`: no sub-batch tiling loss at all); sub-batches only shorten the latency
+        of one batch.
+        The caller promises that `host_in` is ready when the call is made, gives consecutive calls different
+        `host_out` buffers, and waits on the returned event (``ev.synchronize()`` or ``stream.wait_event(ev)``)
+        before reading `host_out`."""
         if host_in.is_cuda or host_out.is_cuda:
             raise RuntimeError("run_host takes host tensors; call the pipeline directly for device tensors")
         B, N = host_in.shape
@@ -174,34 +181,40 @@ class PhaseGenPipeline:
             sizes = [int(c) for c in chunks]
             if sum(sizes) != B or min(sizes) < 1:
                 raise RuntimeError(f"run_host: chunk sizes {sizes} do not add up to the batch of {B}")
-        Bc = max(sizes)
         cur = torch.cuda.current_stream()
         dev = cur.device
         st = getattr(self, "_host_state", None)
-        if st is None or st["key"] != (Bc, N, dev):
-            st = {"key": (Bc, N, dev), "s_in": torch.cuda.Stream(device=dev), "s_out": torch.cuda.Stream(device=dev),
-                  "d_in": [torch.empty(Bc, N, device=dev) for _ in range(2)],
-                  "d_out": [torch.empty(Bc, N, device=dev) for _ in range(2)],
-                  "consumed": [None, None], "drained": [None, None]}
+        key = (tuple(sizes), N, dev)
+        if st is None or st["key"] != key:
+            st = {"key": key, "s_in": torch.cuda.Stream(device=dev), "s_out": torch.cuda.Stream(device=dev), "sets": [], "calls": 0}
             self._host_state = st
-        s_in, s_out = st["s_in"], st["s_out"]
-        s_in.wait_stream(cur)
-        s_out.wait_stream(cur)
+        # the stream-of-batches form alternates between two sets of staging buffers, so the uploads of batch i+1 never
+        # wait for batch i's GPU work (with one sub-batch per batch that is the whole difference between copy + compute
+        # and max(copy, compute)); the one-batch-at-a-time form uses the first set only
+        which = st["calls"] & 1 if pipelined else 0
+        st["calls"] += 1 if pipelined else 0
+        while len(st["sets"]) <= which:
+            st["sets"].append({"d_in": [torch.empty(n, N, device=dev) for n in sizes], "d_out": [torch.empty(n, N, device=dev) for n in sizes],
+                               "consumed": [None] * len(sizes), "drained": [None] * len(sizes)})
+        s_in, s_out, st = st["s_in"], st["s_out"], st["sets"][which]
+        if not pipelined:
+            s_in.wait_stream(cur)
+            s_out.wait_stream(cur)
         c0 = 0
-        for i, n in enumerate(sizes):
+        e_out = None
+        for k, n in enumerate(sizes):
             sl = slice(c0, c0 + n)
             c0 += n
-            k = i & 1
-            d_in, d_out = st["d_in"][k][:n], st["d_out"][k][:n]
+            d_in, d_out = st["d_in"][k], st["d_out"][k]
             if st["consumed"][k] is not None:
-                s_in.wait_event(st["consumed"][k])          # the slot's previous input has been read by its STFT
+                s_in.wait_event(st["consumed"][k])          # the previous batch's sub-batch k has been read by its STFT
             with torch.cuda.stream(s_in):
                 d_in.copy_(host_in[sl], non_blocking=True)
                 e_in = torch.cuda.Event()
                 e_in.record(s_in)
             cur.wait_event(e_in)
             if st["drained"][k] is not None:
-                cur.wait_event(st["drained"][k])            # the slot's previous output has been downloaded
+                cur.wait_event(st["drained"][k])            # the previous batch's output k has been downloaded
             self(d_in, wave_out=d_out)
             e_done = torch.cuda.Event()
             e_done.record(cur)
@@ -212,5 +225,26 @@ class PhaseGenPipeline:
                 e_out = torch.cuda.Event()
                 e_out.record(s_out)
             st["drained"][k] = e_out
+        if pipelined:
+            return e_out                                    # s_out is in order: the last download's event covers them all
         cur.wait_stream(s_out)
         return host_out
+
+
+def ramp_sizes(B, cap, nb, max_waves=6):
+    """Sub-batch sizes [cap(1), cap(2), cap(4), cap(max_waves) ..., cap(4), cap(2), cap(1)] adding up to B (cap(w) = clips whose
+    tiles fill at most w waves; sizes are multiples of nb except possibly one).  Short batches drop the outer steps."""
+    for steps in ((1, 2, 4), (1, 2), (1,)):
+        head = [cap(w) for w in steps]
+        rest = B - 2 * sum(head)
+        if rest >= nb:
+            mid, sizes = cap(max_waves), []
+            while rest > 0:
+                sizes.append(min(mid, rest))
+                rest -= sizes[-1]
+            if len(sizes) > 1 and sizes[-1] < sizes[-2]:    # split the remainder evenly over the last two middles
+                tot = sizes[-1] + sizes[-2]
+                a = (tot // 2 + nb - 1) // nb * nb
+                sizes[-2], sizes[-1] = a, tot - a
+            return head + sizes + head[::-1]
+    return [B]
