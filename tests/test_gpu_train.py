@@ -423,3 +423,27 @@ def test_async_checkpoint_is_a_snapshot_of_the_call_time(tmp_path):
     assert set(got) == set(want)
     for k in want:
         assert torch.equal(got[k], want[k]), k
+
+
+def test_host_batch_feeder_prefetches_in_order():
+    """HostBatchFeeder: batches prefetched from pinned host memory come back in order, each in its own device slot, with
+    the slot of a batch reused only after `done()`; a third prefetch without a `next()` is refused."""
+    from phasegen.train import HostBatchFeeder
+    shape = (3, 16, 64)
+    feeder = HostBatchFeeder(shape, "cuda")
+    hosts = [(torch.full(shape, float(i)).pin_memory(), torch.full(shape, float(-i)).pin_memory()) for i in range(5)]
+    feeder.prefetch(*hosts[0])
+    seen = []
+    for i in range(5):
+        lm, ph = feeder.next()
+        seen.append((float(lm.sum()), float(ph.sum())))          # consumed on the current stream, after the copy
+        feeder.done()
+        if i + 1 < 5:
+            feeder.prefetch(*hosts[i + 1])
+    n = 3 * 16 * 64
+    assert seen == [(float(i * n), float(-i * n)) for i in range(5)]
+    feeder.prefetch(*hosts[0]); feeder.prefetch(*hosts[1])
+    with pytest.raises(RuntimeError, match="not been consumed"):
+        feeder.prefetch(*hosts[2])
+    a, _ = feeder.next()
+    assert float(a.sum()) == 0.0

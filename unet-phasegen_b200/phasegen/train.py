@@ -176,7 +176,9 @@ class TrainStep:
         gradients, update 1/world of (master weights, Adam moments) per rank, all-gather the refreshed operand planes
         (phasegen/sharded.py); False = all-reduce + replicated Adam.  data_parallel=False ignores an initialised process
         group (a purely local step, e.g. a reference replica inside a distributed check).  reserve_ctas: cap of the persistent grids of the
-        backward tensor-core kernels in data-parallel runs (default 132 of 148: 16 SMs stay free for NCCL).
+        backward tensor-core kernels in data-parallel runs (default 148 = no SMs set aside for NCCL: with the sharded optimiser
+        the full grid measured faster at 2 and at 8 GPUs, 8.53 vs 8.62 and 8.45 vs 8.59 ms per step; round 1's all-reduce form
+        wanted 132).
         grad_dtype: dtype of the weight gradients the wgrad kernel writes, NCCL reduces and Adam reads:
         "fp32" (default for the fp32-class precisions: what autograd would give) or "bf16" (default for
         precision="bf16", on any number of GPUs: half the all-reduce volume -- 1.22 GB instead of 2.45 GB for
@@ -205,7 +207,7 @@ class TrainStep:
         self.grad_dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[grad_dtype]
         self.ex = net.train_executor(B, T, device, precision, grad_dtype=self.grad_dtype)
         if self.world > 1 and self.ex.prec != PG_PREC_FP32_SIMT:
-            n_res = int(os.environ.get("PG_DDP_CTAS", "132")) if reserve_ctas is None else int(reserve_ctas)
+            n_res = int(os.environ.get("PG_DDP_CTAS", "148")) if reserve_ctas is None else int(reserve_ctas)
             if 0 < n_res < 148:
                 self.ex.reserve_sms_in_backward(n_res)
         self.t = 0
@@ -418,20 +420,31 @@ class TrainStep:
 class HostBatchFeeder:
     """Uploads (log-magnitude, phase) batches from pinned host memory on a copy stream into two persistent device
     slots, so the H2D copy of batch i+1 overlaps the training step of batch i (train.py:42,49-50,57 upload
-    synchronously every step).  Usage per step: ``lm, ph = feeder.upload(host_lm, host_ph)`` (returns at once,
-    the compute stream is made to wait for the copy), ``loss = step(lm, ph)``, ``feeder.done()``."""
+    synchronously every step).  Usage::
+
+        feeder.prefetch(host_lm, host_ph)              # batch 0, before the loop
+        for ...:
+            lm, ph = feeder.next()                     # the oldest prefetched batch; the compute stream waits for its copy
+            loss = step(lm, ph)
+            feeder.done()                              # this batch's slot may be overwritten once the step has run
+            feeder.prefetch(next_host_lm, next_host_ph)   # travels underneath the step just queued
+
+    ``upload()`` = ``prefetch()`` + ``next()`` for a caller that has nothing to overlap with."""
 
     def __init__(self, shape, device):
         self.dev = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.dev)
         self.slots = [(torch.empty(shape, device=self.dev), torch.empty(shape, device=self.dev)) for _ in range(2)]
         self.free = [None, None]                  # event: the step that read this slot has finished
-        self.i = 0
+        self.ready = []                           # (slot, copy-done event) of prefetched batches, oldest first
+        self.i = 0                                # batches prefetched so far
+        self._k = None
 
-    def upload(self, host_lm, host_ph):
+    def prefetch(self, host_lm, host_ph):
+        if len(self.ready) >= 2:
+            raise RuntimeError("HostBatchFeeder: both device slots hold batches that have not been consumed")
         k = self.i & 1
         lm, ph = self.slots[k]
-        cur = torch.cuda.current_stream(self.dev)
         if self.free[k] is not None:
             self.stream.wait_event(self.free[k])
         with torch.cuda.stream(self.stream):
@@ -439,12 +452,22 @@ class HostBatchFeeder:
             ph.copy_(host_ph, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        cur.wait_event(ev)
+        self.ready.append((k, ev))
+        self.i += 1
+
+    def next(self):
+        if not self.ready:
+            raise RuntimeError("HostBatchFeeder.next(): nothing prefetched")
+        k, ev = self.ready.pop(0)
+        torch.cuda.current_stream(self.dev).wait_event(ev)
         self._k = k
-        return lm, ph
+        return self.slots[k]
+
+    def upload(self, host_lm, host_ph):
+        self.prefetch(host_lm, host_ph)
+        return self.next()
 
     def done(self):
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))
         self.free[self._k] = ev
-        self.i += 1
