@@ -96,25 +96,48 @@ __global__ void bn_finalize_kernel(const float4* __restrict__ stats, int B, int 
 }
 
 // ------------------------------------------------------------------------------- BN + act
+// A thread owns a fixed group of four channels -- its (scale, shift) pairs are read once and live in registers (the first
+// version re-read 32 B of them from L1/L2 for every 16 B of payload) -- and walks rows; four rows are loaded before any is
+// stored so that 64 B per thread are in flight.
 __global__ void __launch_bounds__(256)
 bn_act_kernel(const float* __restrict__ y, int L, int C, int rows, int ld, const float2* __restrict__ scale_shift,
               int per_clip, ActDst d0, ActDst d1) {
     const int c4 = C >> 2;
-    const size_t total = (size_t)L * c4;
     const int b = blockIdx.y;
+    const int tpr = c4 < 256 ? c4 : 256;                    // threads per row (C >= 64 on this path, a multiple of 64)
+    const int rpb = 256 / tpr;                              // rows per CTA pass
+    const int q0 = threadIdx.x % tpr, r = threadIdx.x / tpr;
     const float2* ss = scale_shift ? scale_shift + (size_t)(per_clip ? b : 0) * C : nullptr;
     bool bad0 = false, bad1 = false;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int l = (int)(i / c4), c = (int)(i % c4) * 4;
-        float4 v = *reinterpret_cast<const float4*>(y + ((size_t)b * rows + l) * ld + c);
-        if (ss) {
-            const float4 s01 = *reinterpret_cast<const float4*>(ss + c);
-            const float4 s23 = *reinterpret_cast<const float4*>(ss + c + 2);
-            v.x = fmaf(v.x, s01.x, s01.y); v.y = fmaf(v.y, s01.z, s01.w);
-            v.z = fmaf(v.z, s23.x, s23.y); v.w = fmaf(v.w, s23.z, s23.w);
+    if (r < rpb) {
+        for (int q = q0; q < c4; q += tpr) {                // one pass unless C > 1024
+            const int c = q * 4;
+            float4 s01 = make_float4(1.f, 0.f, 1.f, 0.f), s23 = s01;
+            if (ss) {
+                s01 = __ldg(reinterpret_cast<const float4*>(ss + c));
+                s23 = __ldg(reinterpret_cast<const float4*>(ss + c + 2));
+            }
+            const float* yb = y + (size_t)b * rows * ld + c;
+            const int step = gridDim.x * rpb;
+            for (int l0 = blockIdx.x * rpb + r; l0 < L; l0 += 4 * step) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int l = l0 + u * step;
+                    if (l < L) v[u] = __ldcs(reinterpret_cast<const float4*>(yb + (size_t)l * ld));   // read once: evict first
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int l = l0 + u * step;
+                    if (l >= L) break;
+                    float4 w = v[u];
+                    w.x = fmaf(w.x, s01.x, s01.y); w.y = fmaf(w.y, s01.z, s01.w);
+                    w.z = fmaf(w.z, s23.x, s23.y); w.w = fmaf(w.w, s23.z, s23.w);
+                    if (d0.dtype) bad0 |= store_act4(d0, b, l, c, w);
+                    if (d1.dtype) bad1 |= store_act4(d1, b, l, c, w);
+                }
+            }
         }
-        if (d0.dtype) bad0 |= store_act4(d0, b, l, c, v);
-        if (d1.dtype) bad1 |= store_act4(d1, b, l, c, v);
     }
     if (bad0 && d0.range_flag) atomicOr(d0.range_flag, 1);
     if (bad1 && d1.range_flag) atomicOr(d1.range_flag, 1);
@@ -246,8 +269,12 @@ extern "C" int pg_bn_act(const float* y, int B, int L, int C, int rows, int ld, 
     int rc;
     if ((rc = to_act_dst(dst0, C, &d0, "pg_bn_act", "dst0")) != PG_OK) return rc;
     if ((rc = to_act_dst(dst1, C, &d1, "pg_bn_act", "dst1")) != PG_OK) return rc;
-    const size_t total = (size_t)L * (C / 4);
-    int gx = (int)((total + 255) / 256); if (gx > 1024) gx = 1024;
+    // ~16 CTAs per SM in total: enough to fill the machine, few enough that a thread's (scale, shift) registers pay off
+    const int c4 = C / 4, rpb = 256 / (c4 < 256 ? c4 : 256);
+    int gx = (L + rpb - 1) / rpb;
+    const int want = (148 * 16 + B - 1) / B;
+    if (gx > want) gx = want;
+    if (gx < 1) gx = 1;
     bn_act_kernel<<<dim3(gx, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         y, L, C, rows, ld, reinterpret_cast<const float2*>(scale_shift), per_clip, d0, d1);
     return check_launch("bn_act_kernel");
