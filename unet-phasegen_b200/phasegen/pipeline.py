@@ -192,6 +192,9 @@ class PhaseGenPipeline:
         st = getattr(self, "_host_state", None)
         key = (tuple(sizes), N, dev)
         if st is None or st["key"] != key:
+            if st is not None:                              # a new batch geometry: let the old staging buffers drain before they are freed
+                st["s_in"].synchronize()
+                st["s_out"].synchronize()
             st = {"key": key, "s_in": torch.cuda.Stream(device=dev), "s_out": torch.cuda.Stream(device=dev), "sets": [], "calls": 0}
             self._host_state = st
         # the stream-of-batches form alternates between two sets of staging buffers, so the uploads of batch i+1 never
