@@ -637,7 +637,22 @@ def main():
 
     audio_s = world * B * clip_s
     value = audio_s / (ms / args.steps / 1e3)
-    e2e = audio_s / (ms_e2e / args.steps / 1e3)
+    # both host-buffer call forms are measured in every run (identical copies per step); the headline end-to-end number is the
+    # faster of the two on this host (which one wins depends on the box's PCIe rate), and both are reported
+    forms = {
+        "stream_of_batches": {
+            "value": audio_s / (ms_e2e / args.steps / 1e3), "ms_per_step": ms_e2e / args.steps, "sub_batches": stream_chunks,
+            "form": "run_host(pipelined=True): every step copies its clips in from pinned host memory and its waves back out; the copies of a "
+                    "step run underneath the GPU work of the neighbouring steps (two sets of staging buffers); results awaited by event, "
+                    "alternating pinned output buffers"},
+        "one_batch_at_a_time": {
+            "value": audio_s / (ms_e2e_sync / args.steps / 1e3), "ms_per_step": ms_e2e_sync / args.steps, "sub_batches": e2e_chunks,
+            "form": "run_host(): the call returns with its downloads ordered on the current stream; wave-aligned sub-batches ramp "
+                    "1-2-4-..-4-2-1 waves so the copies hide inside the call"}}
+    best = min(forms, key=lambda k: forms[k]["ms_per_step"])
+    e2e_line = {"value": forms[best]["value"], "unit": UNIT, "h2d_bytes_per_step": B * N * 4, "d2h_bytes_per_step": B * N * 4,
+                "ms_per_step": forms[best]["ms_per_step"], "sub_batches": forms[best]["sub_batches"], "form": best, "forms": forms,
+                "outputs_identical_across_steps": e2e_identical, "host_binding": D.host_binding}
 
     # ---- roofline of the dominant kernel (conv_tc_kernel): CUDA events around every launch
     from phasegen import ops
@@ -793,16 +808,7 @@ def main():
                            "norm_statistics": "per clip (demo.py batch-1 semantics)", "last_layer": "phase-only",
                            "l2_policy": f"inputs larger than L2 ({B * N * 4 / 1e6:.0f} MB wave, >2 GB of activations per step)",
                            "timing": "CUDA events on the launch stream, max over ranks"},
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * N * 4, "d2h_bytes_per_step": B * N * 4,
-                        "ms_per_step": ms_e2e / args.steps, "sub_batches": stream_chunks,
-                        "form": "stream of batches (run_host(pipelined=True)): every step copies its clips in from pinned host memory and its waves "
-                                "back out; the copies of a step run underneath the GPU work of the neighbouring steps (two sets of staging buffers); "
-                                "results awaited by event, alternating pinned output buffers",
-                        "one_batch_at_a_time": {"value": audio_s / (ms_e2e_sync / args.steps / 1e3), "ms_per_step": ms_e2e_sync / args.steps,
-                                                "sub_batches": e2e_chunks,
-                                                "form": "run_host(): the call returns with its downloads ordered on the current stream; "
-                                                        "wave-aligned sub-batches ramp 1-2-4-..-4-2-1 waves so copies hide inside the call"},
-                        "outputs_identical_across_steps": e2e_identical, "host_binding": D.host_binding},
+                "e2e": e2e_line,
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
                 "all_three_product_form": alt, "other_mixed_form": alt1,
                 "gpu_library_baseline": lib, "train": train, "single_clip": single, "longform": longf}
