@@ -731,7 +731,8 @@ def main():
                              "avg_launch_ms": k_ms, "algorithmic_bytes_per_launch": alg[kname],
                              "bytes_moved_per_launch": actual[kname], "frac_of_bytes_moved": actual[kname] / (k_ms / 1e3) / 1e9 / hbm_peak,
                              "traffic": traffic.get(kname, {}).get("bytes_per_launch"),
-                             "note": "issue-bound, not HBM-bound (DESIGN.md 4.2)"})
+                             "note": "not HBM-bound: the STFT is bound by the L1TEX data pipe (shared-memory exchanges + stores, 82 % of peak), "
+                                     "the ISTFT by instruction issue at low occupancy (DESIGN.md 4.2, profiles/r02_stft_pair_experiment.txt)"})
         roof["hbm_kernels"] = roof_hbm
 
     # ---- parity of this run, measured on clips of the timed batch
