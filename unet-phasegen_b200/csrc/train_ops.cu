@@ -54,16 +54,28 @@ phase_loss_kernel(const float* __restrict__ out, const float* __restrict__ logma
     }
 }
 
-__global__ void phase_loss_final_kernel(const double* __restrict__ partial, int n_blocks, double inv_n, float mag_weight,
-                                        float* __restrict__ loss3) {
-    // deterministic: one thread per term walks the block partials in order
-    if (threadIdx.x < 3) {
-        double s = 0.0;
-        for (int b = 0; b < n_blocks; ++b) s += partial[(size_t)b * 3 + threadIdx.x];
-        loss3[1 + threadIdx.x] = (float)(s * inv_n);
+__global__ void __launch_bounds__(256)
+phase_loss_final_kernel(const double* __restrict__ partial, int n_blocks, double inv_n, float mag_weight,
+                        float* __restrict__ loss3) {
+    // deterministic: thread t sums the block partials t, t + 256, ... in order, then a fixed tree over the 256 sums
+    // (one thread walking all partials took 57 us per step)
+    __shared__ double sh[3][256];
+    const int t = threadIdx.x;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int b = t; b < n_blocks; b += 256) {
+        s0 += partial[(size_t)b * 3 + 0]; s1 += partial[(size_t)b * 3 + 1]; s2 += partial[(size_t)b * 3 + 2];
     }
+    sh[0][t] = s0; sh[1][t] = s1; sh[2][t] = s2;
     __syncthreads();
-    if (threadIdx.x == 0) loss3[0] = loss3[1] + loss3[2] + mag_weight * loss3[3];
+    for (int o = 128; o > 0; o >>= 1) {
+        if (t < o) { sh[0][t] += sh[0][t + o]; sh[1][t] += sh[1][t + o]; sh[2][t] += sh[2][t + o]; }
+        __syncthreads();
+    }
+    if (t == 0) {
+        const float a = (float)(sh[0][0] * inv_n), b = (float)(sh[1][0] * inv_n), c = (float)(sh[2][0] * inv_n);
+        loss3[1] = a; loss3[2] = b; loss3[3] = c;
+        loss3[0] = a + b + mag_weight * c;
+    }
 }
 
 // ------------------------------------------------------------------------------ BN backward
@@ -276,7 +288,7 @@ extern "C" int pg_phase_loss(const float* out, const float* logmag, const float*
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const double inv_n = 1.0 / ((double)rows * C);
     phase_loss_kernel<<<n_blocks, 256, 0, st>>>(out, logmag, phase, rows, C, (float)inv_n, mag_weight, d_out, partial);
-    phase_loss_final_kernel<<<1, 32, 0, st>>>(partial, n_blocks, inv_n, mag_weight, loss3);
+    phase_loss_final_kernel<<<1, 256, 0, st>>>(partial, n_blocks, inv_n, mag_weight, loss3);
     return check_launch("phase_loss_kernel");
 }
 

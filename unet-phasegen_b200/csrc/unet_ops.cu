@@ -71,6 +71,10 @@ __global__ void channel_stats_kernel(const float* __restrict__ y, int L, int C, 
 }
 
 // --------------------------------------------------------------------------- BN finalize
+// Pooled statistics of the records {n_i, mean_i, M2_i} in double, two passes: mean = sum n_i mean_i / N, then
+// M2 = sum (M2_i + n_i (mean_i - mean)^2) -- Chan's combination without a division inside the loop.  (The first version merged
+// the records one by one with two dependent fp64 divisions per record: 37 us per launch for the 64-128 records of a training
+// batch, 0.22 ms per training step in six launches.)  The loads of a pass are independent, so they are issued in batches of 8.
 __global__ void bn_finalize_kernel(const float4* __restrict__ stats, int B, int P, int C, int per_clip,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float2* __restrict__ scale_shift, float2* __restrict__ mean_var) {
@@ -78,16 +82,21 @@ __global__ void bn_finalize_kernel(const float4* __restrict__ stats, int B, int 
     const int g = blockIdx.y;
     if (c >= C) return;
     const int b0 = per_clip ? g : 0, b1 = per_clip ? g + 1 : B;
-    double n = 0.0, mean = 0.0, m2 = 0.0;
-    for (int b = b0; b < b1; ++b)
-        for (int p = 0; p < P; ++p) {
-            const float4 r = stats[((size_t)b * P + p) * C + c];
-            if (r.x <= 0.f) continue;
-            const double nb = r.x, d = (double)r.y - mean, nn = n + nb;
-            mean += d * nb / nn;
-            m2 += (double)r.z + d * d * n * nb / nn;
-            n = nn;
-        }
+    const float4* rec = stats + (size_t)b0 * P * C + c;
+    const int R = (b1 - b0) * P;                            // records of channel c, C apart
+    double n = 0.0, s = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < R; ++r) {
+        const float4 q = __ldg(rec + (size_t)r * C);
+        if (q.x > 0.f) { n += (double)q.x; s += (double)q.x * (double)q.y; }
+    }
+    const double mean = n > 0.0 ? s / n : 0.0;
+    double m2 = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < R; ++r) {
+        const float4 q = __ldg(rec + (size_t)r * C);
+        if (q.x > 0.f) { const double d = (double)q.y - mean; m2 += (double)q.z + (double)q.x * d * d; }
+    }
     const double var = n > 0.0 ? m2 / n : 0.0;
     const double sc = (gamma ? (double)gamma[c] : 1.0) / sqrt(var + (double)eps);
     const double sh = (beta ? (double)beta[c] : 0.0) - mean * sc;
