@@ -179,6 +179,11 @@ int pg_channel_stats(const float* y, int B, int L, int C, int rows, int ld, floa
 int pg_bn_finalize(const float* stats, int B, int P, int C, int per_clip, const float* gamma,
                    const float* beta, float eps, float* scale_shift, float* mean_var, pg_stream stream);
 
+/* Train-mode side effect of nn.BatchNorm (model.py:81,83 in train mode): running = (1 - momentum) * running + momentum * batch value,
+ * the variance unbiased by `unbias` = n / (n - 1).  mean_var: float2 [C] (mean, biased variance) as written by pg_bn_finalize. */
+int pg_bn_running_update(const float* mean_var, float* running_mean, float* running_var, int C, float momentum, float unbias,
+                         pg_stream stream);
+
 /* eval-mode norm (nn.BatchNorm after .eval(); the reference never calls it, kept for API parity): scale/shift from the
  * running statistics, replicated into G groups so that per-clip consumers can index it by clip. */
 int pg_bn_from_running(const float* running_mean, const float* running_var, const float* gamma, const float* beta,

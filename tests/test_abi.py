@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/phasegen.h but not exported"
     assert set(_lib.EXPORTS) == set(syms), "ctypes binding and header disagree"
-    assert _lib.load().pg_abi_version() == _lib.ABI_VERSION == 3
+    assert _lib.load().pg_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_struct_layouts_match_header():

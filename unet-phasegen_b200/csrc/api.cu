@@ -26,7 +26,7 @@ int check_launch(const char* what) {
 }  // namespace pg
 
 extern "C" const char* pg_last_error(void) { return pg::g_err; }
-extern "C" int pg_abi_version(void) { return 3; }
+extern "C" int pg_abi_version(void) { return 4; }
 
 extern "C" int pg_check_device(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0, n = 0;

@@ -152,6 +152,16 @@ bn_act_kernel(const float* __restrict__ y, int L, int C, int rows, int ld, const
     if (bad1 && d1.range_flag) atomicOr(d1.range_flag, 1);
 }
 
+// momentum update of the running buffers from the batch statistics (train-mode nn.BatchNorm side effect)
+__global__ void bn_running_update_kernel(const float2* __restrict__ mean_var, float* __restrict__ running_mean,
+                                         float* __restrict__ running_var, int C, float momentum, float unbias) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float2 mv = mean_var[c];
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mv.x;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (mv.y * unbias);
+}
+
 // eval-mode norm (nn.BatchNorm with running statistics): scale = gamma / sqrt(running_var + eps), shift = beta - mean*scale
 __global__ void bn_from_running_kernel(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float eps, int C, int G, float2* __restrict__ scale_shift,
@@ -298,6 +308,14 @@ extern "C" int pg_pack_weight(const float* w, int kind, int C_in, int C_out, int
     pack_weight_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         w, kind == PG_CONV_TRANSPOSE, C_in, C_out, k, w_hi, w_lo, w_simt, fmt);
     return check_launch("pack_weight_kernel");
+}
+
+extern "C" int pg_bn_running_update(const float* mean_var, float* running_mean, float* running_var, int C, float momentum,
+                                    float unbias, pg_stream stream) {
+    PG_REQUIRE(mean_var && running_mean && running_var && C > 0, "pg_bn_running_update: bad arguments");
+    bn_running_update_kernel<<<(C + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2*>(mean_var), running_mean, running_var, C, momentum, unbias);
+    return check_launch("bn_running_update_kernel");
 }
 
 extern "C" int pg_bn_from_running(const float* running_mean, const float* running_var, const float* gamma, const float* beta,

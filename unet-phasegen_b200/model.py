@@ -310,6 +310,8 @@ class UNetModel(nn.Module):
 
     def _update_running_stats(self, ex):
         """Train-mode side effect of nn.BatchNorm (momentum update of the running buffers)."""
+        from phasegen import ops
+        counters = []
         for i, b in enumerate(self._blocks()):
             for m, mv, desc in ((b._parts["down_norm"], ex.dn_mv[i], ex.dn_desc[i]), (b._parts["up_norm"], ex.up_mv[i], ex.up_desc[i])):
                 if m is None or mv is None or not getattr(m, "track_running_stats", False) or m.running_mean is None:
@@ -319,9 +321,15 @@ class UNetModel(nn.Module):
                 n = desc.B * desc.L_out
                 mom = m.momentum if m.momentum is not None else 0.1
                 with torch.no_grad():
-                    m.running_mean.mul_(1 - mom).add_(mv[0, :, 0], alpha=mom)
-                    m.running_var.mul_(1 - mom).add_(mv[0, :, 1] * (n / max(n - 1, 1)), alpha=mom)
-                    m.num_batches_tracked += 1
+                    if m.running_mean.dtype == torch.float32 and m.running_mean.is_contiguous() and m.running_var.is_contiguous():
+                        ops.bn_running_update(mv, m.running_mean, m.running_var, mom, n / max(n - 1, 1))   # one launch per norm
+                    else:
+                        m.running_mean.mul_(1 - mom).add_(mv[0, :, 0], alpha=mom)
+                        m.running_var.mul_(1 - mom).add_(mv[0, :, 1] * (n / max(n - 1, 1)), alpha=mom)
+                    counters.append(m.num_batches_tracked)
+        if counters:
+            with torch.no_grad():
+                torch._foreach_add_(counters, 1)                 # one launch for every norm's step counter
 
     # -------------------------------------------------------------------------- public API
     def forward(self, input, per_clip=False):

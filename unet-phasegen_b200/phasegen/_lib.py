@@ -16,7 +16,7 @@ PG_FMT_BF16, PG_FMT_F16 = 0, 1
 PG_STFT_LOGMAG, PG_STFT_REIM, PG_STFT_PROJECT, PG_STFT_PAIRS = 0, 1, 2, 3
 PG_SPEC_POLAR_LOG, PG_SPEC_CARTESIAN, PG_SPEC_POLAR_MAG = 0, 1, 2
 PG_EPI_RAW, PG_EPI_ACT, PG_EPI_NORM_ACT = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # "f16mix" is an executor-level name (phasegen/unet.py): fp16 planes everywhere, the three-product
 # form on the small layers and the two-product form (fp16-rounded weights) on the three largest.
@@ -62,6 +62,7 @@ _SIGNATURES = {
     "pg_pack_weight": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "pg_conv_tc": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, C.POINTER(ConvEpilogue), _P]),
     "pg_conv_epilogue_supported": (_I, [C.POINTER(ConvDesc), _I]),
+    "pg_bn_running_update": (_I, [_P, _P, _P, _I, _F, _F, _P]),
     "pg_bn_from_running": (_I, [_P, _P, _P, _P, _F, _I, _I, _P, _P, _P]),
     "pg_conv_stat_parts": (_I, [C.POINTER(ConvDesc)]),
     "pg_conv_tc_plan": (_I, [C.POINTER(ConvDesc), C.POINTER(_I), _I]),

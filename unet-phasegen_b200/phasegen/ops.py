@@ -254,6 +254,19 @@ def act_dst(hi, lo, batch_stride, ld, ch_off, dtype, slope, range_flag=None):
                   batch_stride, ld, ch_off, dtype, slope, range_flag.data_ptr() if range_flag is not None else None)
 
 
+def bn_running_update(mean_var, running_mean, running_var, momentum, unbias):
+    """running = (1 - momentum) * running + momentum * batch statistic (variance times `unbias`), in place, one launch.
+    mean_var: float32 [.., C, 2] as written by bn_finalize (its first group is used)."""
+    Cn = running_mean.numel()
+    for t, name in ((mean_var, "mean_var"), (running_mean, "running_mean"), (running_var, "running_var")):
+        _need_cuda(t, name)
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError(f"phasegen.bn_running_update: {name} must be a contiguous float32 CUDA tensor")
+    if mean_var.numel() < 2 * Cn or running_var.numel() != Cn:
+        raise RuntimeError("phasegen.bn_running_update: shapes do not match")
+    _lib.call("pg_bn_running_update", _ptr(mean_var), _ptr(running_mean), _ptr(running_var), Cn, float(momentum), float(unbias), _stream())
+
+
 def bn_from_running(running_mean, running_var, gamma, beta, eps, scale_shift, mean_var=None):
     """eval-mode norm: (scale, shift) from the running statistics, replicated over the G rows of scale_shift [G, C, 2]."""
     G, Cn = scale_shift.shape[0], scale_shift.shape[1]
